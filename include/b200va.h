@@ -1,0 +1,165 @@
+/*
+ * b200va.h -- C ABI of libb200va.so: the B200 (sm_100a) vectorAdd hot path.
+ *
+ * The reference (ashrafgt/k8s-gpu-hpa) has NO library/plugin API for this path: the
+ * kernel is statically linked into the `vectorAdd` executable inside the third-party
+ * image k8s.gcr.io/cuda-vector-add:v0.1, and the reference only invokes it:
+ *
+ *     image:   "k8s.gcr.io/cuda-vector-add:v0.1"                     cuda-test-deployment.yaml:18
+ *     command: for (( c=1; c<=5000; c++ )); do ./vectorAdd; done     cuda-test-deployment.yaml:19
+ *     (same loop started by hand to raise utilisation)               README.md:113-116
+ *
+ * The outer drop-in boundary is therefore the `vectorAdd` executable
+ * (k8s-gpu-hpa_b200/host/vectorAdd.cpp).  This header is the inner boundary the
+ * executable -- and any other host language via cgo/JNI/ctypes -- binds: each entry
+ * point below names the step of that process it
+ * replaces.  See INTEGRATION.md for the binding stubs.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ or torch types, no exceptions.
+ *   - Functions return 0 (B200VA_OK) or a negative code; they never print or abort.
+ *     CUDA runtime failures are returned as  -(1000 + cudaError_t).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Device entry points are asynchronous on that stream: no hidden synchronisation,
+ *     no hidden allocation; the caller owns every buffer.
+ *   - The current CUDA device of the calling thread is used (cudaSetDevice first);
+ *     the library is re-entrant and keeps only immutable per-device attribute caches.
+ *   - Element type is IEEE-754 binary32; the add is add.rn.f32 without FTZ, so results
+ *     are bit-identical to a scalar C loop on the same inputs (NaN payloads excepted:
+ *     PTX returns the canonical NaN 0x7fffffff).
+ */
+#ifndef B200VA_H
+#define B200VA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VA_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------- */
+#define B200VA_OK               0
+#define B200VA_ERR_INVALID     (-1)   /* NULL pointer with n > 0, bad argument            */
+#define B200VA_ERR_ALIGN       (-2)   /* pointer not 4-byte aligned                       */
+#define B200VA_ERR_OVERLAP     (-3)   /* C partially overlaps A or B (exact alias is ok)  */
+#define B200VA_ERR_VARIANT     (-4)   /* unknown kernel variant / unsupported tune combo  */
+#define B200VA_ERR_NO_DEVICE   (-5)   /* no CUDA device / not an sm_100 device            */
+#define B200VA_ERR_VERIFY      (-6)   /* result verification failed (a6)                  */
+#define B200VA_ERR_NOMEM       (-7)   /* host allocation failed                           */
+#define B200VA_ERR_CUDA_BASE   (-1000) /* code = -(1000 + cudaError_t)                    */
+
+/* ---- kernel variants (argument `variant`) ---------------------------------------- */
+#define B200VA_K_AUTO      0   /* the tuned production choice for this n                */
+#define B200VA_K0_SCALAR   1   /* reference-shape control: 1 elem/thread, 256-thread CTAs,
+                                  (n+255)/256 CTAs  (CUDA sample launch geometry, a5)   */
+#define B200VA_K1_VEC128   2   /* 128-bit ld/st.global.v4.f32, unrolled, cache-hinted   */
+#define B200VA_K2_TMA      3   /* persistent CTAs, cp.async.bulk (TMA) smem ring        */
+#define B200VA_K3_VEC256   4   /* 256-bit ld/st.global.v8.f32 (PTX 8.8, sm_100)         */
+
+/* Explicit geometry for A/B experiments (b200va_add_f32_tuned). Zero = default.      */
+typedef struct b200va_tune {
+    int kind;         /* B200VA_K0_SCALAR .. B200VA_K3_VEC256                           */
+    int threads;      /* CTA size (vec kernels) or consumer threads (TMA kernel)        */
+    int unroll;       /* vec: vectors per thread per tile: 1,2,4,8                      */
+    int ctas_per_sm;  /* 0: one tile per CTA; >0: persistent grid = SMs * ctas_per_sm   */
+    int ld_hint;      /* 0 plain, 1 L1::no_allocate, 2 .cs, 3 no_allocate+L2 evict_first, 4 .nc+no_allocate */
+    int st_hint;      /* 0 plain, 1 L1::no_allocate,   2 .cs, 3 no_allocate+L2 evict_first */
+    int stages;       /* TMA: ring depth (2..16)                                        */
+    int tile_bytes;   /* TMA: bytes per array per stage (multiple of 2048)              */
+    int store_mode;   /* TMA: 0 = st.global from registers, 1 = bulk store from smem    */
+} b200va_tune_t;
+
+typedef struct b200va_devinfo {
+    int device;
+    int cc_major, cc_minor;
+    int sm_count;
+    int max_smem_optin;        /* bytes                                                 */
+    int l2_bytes;
+    size_t global_mem_bytes;
+    char name[64];
+} b200va_devinfo_t;
+
+/* ---- library ----------------------------------------------------------------------- */
+int         b200va_abi_version(void);
+const char *b200va_strerror(int code);
+/* Attributes of `device` (does not change the current device). */
+int         b200va_query(int device, b200va_devinfo_t *out);
+/* The geometry B200VA_K_AUTO (or a named variant) resolves to for n elements. */
+int         b200va_resolve(int variant, size_t n, b200va_tune_t *out);
+
+/* Launch geometry a tune resolves to on `device` for n elements with 32-byte-aligned
+ * pointers (what "CUDA kernel launch with %d blocks of %d threads" prints, a5). */
+int         b200va_geometry(const b200va_tune_t *tune, size_t n, int device,
+                            unsigned *grid, unsigned *block, unsigned *dyn_smem_bytes);
+
+/* ---- a4 + a5: the vectorAdd kernel and its launch geometry -------------------------
+ * Replaces `vectorAdd<<<blocksPerGrid, threadsPerBlock>>>(d_A, d_B, d_C, numElements)`
+ * of the image's binary (invoked at cuda-test-deployment.yaml:19).
+ * dA, dB, dC: device pointers, 4-byte aligned; any n >= 0; dC may equal dA or dB. */
+int b200va_add_f32(const float *dA, const float *dB, float *dC, size_t n,
+                   int variant, void *stream);
+int b200va_add_f32_tuned(const float *dA, const float *dB, float *dC, size_t n,
+                         const b200va_tune_t *tune, void *stream);
+
+/* ---- a1: the launch loop, in-process -----------------------------------------------
+ * Replaces the 5000-process bash loop (cuda-test-deployment.yaml:19): `iters`
+ * back-to-back launches on `stream`; graph_batch > 1 captures that many launches into
+ * one CUDA graph and replays it (launch-bound sizes).  Asynchronous. */
+int b200va_add_f32_loop(const float *dA, const float *dB, float *dC, size_t n,
+                        int variant, int iters, int graph_batch, void *stream);
+
+/* ---- a2: input recipes ---------------------------------------------------------------
+ * Host: the sample's recipe  h_A[i] = rand()/(float)RAND_MAX; h_B[i] = ... interleaved,
+ * never seeded.  Reseeds glibc to 1 so every call equals a fresh ./vectorAdd process. */
+int b200va_host_fill_rand_f32(float *hA, float *hB, size_t n);
+/* Counter generator for large n (index-addressable, shard-invariant):
+ * x[i] = (float)(splitmix64(seed*0x9E3779B97F4A7C15 + first + i) >> 40) * 2^-24.       */
+int b200va_host_fill_ctr_f32(float *h, size_t n, uint64_t seed, uint64_t first);
+int b200va_fill_ctr_f32(float *d, size_t n, uint64_t seed, uint64_t first, void *stream);
+
+/* ---- a6: verification ----------------------------------------------------------------
+ * Host: the sample's check made strict: bitwise C[i] == A[i]+B[i] (NaNs as a class).
+ * Returns B200VA_OK or B200VA_ERR_VERIFY with *first_bad = failing index.            */
+int b200va_host_verify_f32(const float *hA, const float *hB, const float *hC, size_t n,
+                           size_t *first_bad);
+/* Device: recompute + bit-compare in HBM.  d_result[0] = mismatch count,
+ * d_result[1] = first mismatching index (UINT64_MAX if none).  Asynchronous; the
+ * caller zero-inits nothing (the call resets d_result on the stream first).          */
+int b200va_verify_f32(const float *dA, const float *dB, const float *dC, size_t n,
+                      uint64_t *d_result, void *stream);
+/* Device digest of a vector's bit patterns: d_out[0] = sum of uint32 patterns mod 2^64,
+ * d_out[1] = xor of them.  Order-independent, so shards combine by + and ^.          */
+int b200va_digest_f32(const float *d, size_t n, uint64_t *d_out, void *stream);
+
+/* ---- a3 + a4 + a6(copy) : host-buffer path -------------------------------------------
+ * Replaces cudaMalloc x3 / cudaMemcpy H2D x2 / kernel / cudaMemcpy D2H of one
+ * ./vectorAdd run, for host arrays of any size: a staged, double-direction pipeline
+ * (H2D of chunk k+1, add of chunk k, D2H of chunk k-1 overlap on separate streams).
+ * A stager owns its device staging buffers and streams; create one per device/thread. */
+typedef struct b200va_stager b200va_stager_t;
+/* mode 0: copy-engine pipeline through HBM staging buffers;
+ * mode 1: zero-copy kernel reading/writing pinned host memory directly over PCIe
+ *         (requires all three host buffers pinned/registered).                        */
+int b200va_stager_create(b200va_stager_t **out, int device, size_t chunk_elems, int depth);
+int b200va_stager_add_f32(b200va_stager_t *s, const float *hA, const float *hB, float *hC,
+                          size_t n, int variant, int mode);
+/* Device-side time of the last b200va_stager_add_f32 call, milliseconds (events). */
+int b200va_stager_last_ms(b200va_stager_t *s, float *ms);
+int b200va_stager_destroy(b200va_stager_t *s);
+/* One-shot convenience: create, add, destroy (synchronous). */
+int b200va_add_f32_host(const float *hA, const float *hB, float *hC, size_t n,
+                        int device, int variant);
+/* Pinned host memory for the pipeline (cudaHostAlloc / cudaFreeHost). */
+int b200va_host_alloc(void **out, size_t bytes);
+int b200va_host_free(void *p);
+
+/* ---- shard arithmetic (8(e)): contiguous equal shards, starts on 16-byte multiples --- */
+int b200va_shard_range(size_t n, int world, int rank, size_t *begin, size_t *end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VA_H */

@@ -1,0 +1,115 @@
+"""ctypes binding of libb200va.so -- one Python function per symbol of include/b200va.h.
+
+This is the same stub a maintainer would write for any other host language (see
+INTEGRATION.md): plain pointers and sizes across the boundary.  The library is built
+in-tree by ``make -C k8s-gpu-hpa_b200`` (``__graft_entry__.build()``); if it is missing
+the import fails loudly -- there is no Python/CPU fallback for the hot path.
+
+Reference interface replaced: the ``./vectorAdd`` process of
+``cuda-test-deployment.yaml:18-19``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200va.so")
+CLI_PATH = os.path.join(_HERE, "vectorAdd")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200va.h")
+
+OK = 0
+ERR_INVALID, ERR_ALIGN, ERR_OVERLAP, ERR_VARIANT, ERR_NO_DEVICE, ERR_VERIFY, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
+ERR_CUDA_BASE = -1000
+K_AUTO, K0_SCALAR, K1_VEC128, K2_TMA, K3_VEC256 = 0, 1, 2, 3, 4
+VARIANTS = {"auto": K_AUTO, "k0": K0_SCALAR, "k1": K1_VEC128, "k2": K2_TMA, "k3": K3_VEC256}
+
+
+class B200VAError(RuntimeError):
+    def __init__(self, code: int, what: str = ""):
+        self.code = code
+        super().__init__(f"{what + ': ' if what else ''}{strerror(code)} ({code})")
+
+
+class Tune(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("kind", "threads", "unroll", "ctas_per_sm", "ld_hint", "st_hint",
+                                       "stages", "tile_bytes", "store_mode")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class DevInfo(C.Structure):
+    _fields_ = [("device", C.c_int), ("cc_major", C.c_int), ("cc_minor", C.c_int), ("sm_count", C.c_int),
+                ("max_smem_optin", C.c_int), ("l2_bytes", C.c_int), ("global_mem_bytes", C.c_size_t),
+                ("name", C.c_char * 64)]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `make -C {_HERE}` (or __graft_entry__.build()). "
+        "The vectorAdd hot path has no fallback implementation.")
+
+lib = C.CDLL(LIB_PATH)
+
+_P, _SZ, _I, _U64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+_SIGS = {
+    "b200va_abi_version": (_I, []),
+    "b200va_strerror": (C.c_char_p, [_I]),
+    "b200va_query": (_I, [_I, C.POINTER(DevInfo)]),
+    "b200va_resolve": (_I, [_I, _SZ, C.POINTER(Tune)]),
+    "b200va_geometry": (_I, [C.POINTER(Tune), _SZ, _I, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
+    "b200va_add_f32": (_I, [_P, _P, _P, _SZ, _I, _P]),
+    "b200va_add_f32_tuned": (_I, [_P, _P, _P, _SZ, C.POINTER(Tune), _P]),
+    "b200va_add_f32_loop": (_I, [_P, _P, _P, _SZ, _I, _I, _I, _P]),
+    "b200va_host_fill_rand_f32": (_I, [_P, _P, _SZ]),
+    "b200va_host_fill_ctr_f32": (_I, [_P, _SZ, _U64, _U64]),
+    "b200va_fill_ctr_f32": (_I, [_P, _SZ, _U64, _U64, _P]),
+    "b200va_host_verify_f32": (_I, [_P, _P, _P, _SZ, C.POINTER(_SZ)]),
+    "b200va_verify_f32": (_I, [_P, _P, _P, _SZ, _P, _P]),
+    "b200va_digest_f32": (_I, [_P, _SZ, _P, _P]),
+    "b200va_stager_create": (_I, [C.POINTER(_P), _I, _SZ, _I]),
+    "b200va_stager_add_f32": (_I, [_P, _P, _P, _P, _SZ, _I, _I]),
+    "b200va_stager_last_ms": (_I, [_P, C.POINTER(C.c_float)]),
+    "b200va_stager_destroy": (_I, [_P]),
+    "b200va_add_f32_host": (_I, [_P, _P, _P, _SZ, _I, _I]),
+    "b200va_host_alloc": (_I, [C.POINTER(_P), _SZ]),
+    "b200va_host_free": (_I, [_P]),
+    "b200va_shard_range": (_I, [_SZ, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
+}
+for _name, (_res, _args) in _SIGS.items():
+    _f = getattr(lib, _name)          # AttributeError here = header/library mismatch
+    _f.restype, _f.argtypes = _res, _args
+
+EXPORTED = tuple(_SIGS)
+
+
+def strerror(code: int) -> str:
+    return lib.b200va_strerror(code).decode()
+
+
+def check(code: int, what: str = "") -> None:
+    if code != OK:
+        raise B200VAError(code, what)
+
+
+def abi_version() -> int:
+    return lib.b200va_abi_version()
+
+
+def query(device: int = 0) -> DevInfo:
+    info = DevInfo()
+    check(lib.b200va_query(device, C.byref(info)), "b200va_query")
+    return info
+
+
+def resolve(variant: int, n: int) -> Tune:
+    t = Tune()
+    check(lib.b200va_resolve(variant, n, C.byref(t)), "b200va_resolve")
+    return t
+
+
+def shard_range(n: int, world: int, rank: int) -> tuple[int, int]:
+    b, e = _SZ(), _SZ()
+    check(lib.b200va_shard_range(n, world, rank, C.byref(b), C.byref(e)), "b200va_shard_range")
+    return b.value, e.value

@@ -1,0 +1,698 @@
+// b200va_capi.cu -- the C ABI of libb200va.so (declared in include/b200va.h).
+//
+// Host-side dispatch for the sm_100a vectorAdd kernels: argument checking, alignment
+// peeling, geometry resolution, the in-process launch loop, the host-buffer staging
+// pipeline.  Each entry point names the step of the reference's `./vectorAdd` process
+// it replaces (cuda-test-deployment.yaml:18-19).
+//
+// There is deliberately NO CPU fallback: without a CUDA device every compute entry
+// point returns an error code.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "../../include/b200va.h"
+#include "b200va_kernels.cuh"
+
+using namespace b200va;
+
+namespace {
+
+constexpr int kMaxDevices = 64;
+
+inline int cuda_err(cudaError_t e) { return e == cudaSuccess ? B200VA_OK : -(1000 + static_cast<int>(e)); }
+
+#define CU_TRY(expr)                                   \
+    do {                                               \
+        cudaError_t e__ = (expr);                      \
+        if (e__ != cudaSuccess) return cuda_err(e__);  \
+    } while (0)
+
+#define RC_TRY(expr)                   \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != B200VA_OK) return rc__; \
+    } while (0)
+
+struct DevCache {
+    std::once_flag once;
+    int rc = B200VA_ERR_NO_DEVICE;
+    b200va_devinfo_t info{};
+};
+DevCache g_dev[kMaxDevices];
+
+int dev_info(int device, const b200va_devinfo_t** out)
+{
+    if (device < 0 || device >= kMaxDevices) return B200VA_ERR_INVALID;
+    DevCache& dc = g_dev[device];
+    std::call_once(dc.once, [&] {
+        cudaDeviceProp p;
+        cudaError_t e = cudaGetDeviceProperties(&p, device);
+        if (e != cudaSuccess) { dc.rc = cuda_err(e); return; }
+        dc.info.device = device;
+        dc.info.cc_major = p.major;
+        dc.info.cc_minor = p.minor;
+        dc.info.sm_count = p.multiProcessorCount;
+        dc.info.max_smem_optin = static_cast<int>(p.sharedMemPerBlockOptin);
+        dc.info.l2_bytes = p.l2CacheSize;
+        dc.info.global_mem_bytes = p.totalGlobalMem;
+        std::snprintf(dc.info.name, sizeof dc.info.name, "%s", p.name);
+        dc.rc = (p.major == 10) ? B200VA_OK : B200VA_ERR_NO_DEVICE;
+    });
+    if (out) *out = &dc.info;
+    return dc.rc;
+}
+
+int current_dev_info(const b200va_devinfo_t** out)
+{
+    int device = -1;
+    CU_TRY(cudaGetDevice(&device));
+    return dev_info(device, out);
+}
+
+// ----------------------------------------------------------------------- vec dispatch
+using vec_fn = void (*)(const float*, const float*, float*, size_t, size_t, size_t, size_t);
+
+template <int VW, int UNROLL, int LD>
+vec_fn pick_st(int st)
+{
+    switch (st) {
+        case ST_PLAIN: return vadd_vec<VW, UNROLL, LD, ST_PLAIN>;
+        case ST_NA:    return vadd_vec<VW, UNROLL, LD, ST_NA>;
+        case ST_CS:    return vadd_vec<VW, UNROLL, LD, ST_CS>;
+        case ST_NA_EF: return vadd_vec<VW, UNROLL, LD, ST_NA_EF>;
+    }
+    return nullptr;
+}
+
+template <int VW, int UNROLL>
+vec_fn pick_ld(int ld, int st)
+{
+    switch (ld) {
+        case LD_PLAIN: return pick_st<VW, UNROLL, LD_PLAIN>(st);
+        case LD_NA:    return pick_st<VW, UNROLL, LD_NA>(st);
+        case LD_NC_NA: return pick_st<VW, UNROLL, LD_NC_NA>(st);
+        case LD_CS:    return pick_st<VW, UNROLL, LD_CS>(st);
+        case LD_NA_EF: return pick_st<VW, UNROLL, LD_NA_EF>(st);
+    }
+    return nullptr;
+}
+
+template <int VW>
+vec_fn pick_unroll(int unroll, int ld, int st)
+{
+    switch (unroll) {
+        case 1: return pick_ld<VW, 1>(ld, st);
+        case 2: return pick_ld<VW, 2>(ld, st);
+        case 4: return pick_ld<VW, 4>(ld, st);
+        case 8: return pick_ld<VW, 8>(ld, st);
+    }
+    return nullptr;
+}
+
+vec_fn pick_vec(int vw, int unroll, int ld, int st)
+{
+    return vw == 8 ? pick_unroll<8>(unroll, ld, st) : pick_unroll<4>(unroll, ld, st);
+}
+
+// ----------------------------------------------------------------------- tma dispatch
+using tma_fn = void (*)(const float*, const float*, float*, size_t, size_t, size_t, uint32_t, uint32_t);
+
+template <int MODE, bool HINT>
+tma_fn pick_tma_st(int st)
+{
+    switch (st) {
+        case ST_PLAIN: return vadd_tma<MODE, HINT, ST_PLAIN>;
+        case ST_NA:    return vadd_tma<MODE, HINT, ST_NA>;
+        case ST_CS:    return vadd_tma<MODE, HINT, ST_CS>;
+        case ST_NA_EF: return vadd_tma<MODE, HINT, ST_NA_EF>;
+    }
+    return nullptr;
+}
+
+tma_fn pick_tma(int store_mode, bool l2_hint, int st)
+{
+    if (store_mode == 1)  // st hint is meaningless for bulk stores: one instantiation
+        return l2_hint ? vadd_tma<1, true, ST_PLAIN> : vadd_tma<1, false, ST_PLAIN>;
+    return l2_hint ? pick_tma_st<0, true>(st) : pick_tma_st<0, false>(st);
+}
+
+std::mutex g_attr_mu;
+
+// Opt in to > 48 KiB dynamic shared memory once per (function, device).
+int ensure_smem_optin(tma_fn fn, int device, int bytes)
+{
+    struct Key { tma_fn fn; int device; int bytes; };
+    static Key seen[256];
+    static int n_seen = 0;
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i].fn == fn && seen[i].device == device) {
+            if (seen[i].bytes >= bytes) return B200VA_OK;
+            CU_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn),
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            seen[i].bytes = bytes;
+            return B200VA_OK;
+        }
+    CU_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (n_seen < 256) seen[n_seen++] = Key{fn, device, bytes};
+    return B200VA_OK;
+}
+
+// ----------------------------------------------------------------------- geometry
+// Production choices per size class.  Tuned on B200 (profiles/): see DESIGN.md.
+void default_tune(int variant, size_t n, b200va_tune_t* t)
+{
+    std::memset(t, 0, sizeof *t);
+    switch (variant) {
+        case B200VA_K0_SCALAR:
+            t->kind = B200VA_K0_SCALAR;
+            t->threads = 256;
+            t->unroll = 1;
+            return;
+        case B200VA_K2_TMA:
+            t->kind = B200VA_K2_TMA;
+            t->threads = 256;          // consumer threads (+32 producer)
+            t->ctas_per_sm = 1;
+            t->ld_hint = LD_PLAIN;
+            t->st_hint = ST_NA;
+            t->stages = 6;
+            t->tile_bytes = 16384;
+            t->store_mode = 1;
+            return;
+        case B200VA_K1_VEC128:
+            t->kind = B200VA_K1_VEC128;
+            break;
+        case B200VA_K3_VEC256:
+        case B200VA_K_AUTO:
+        default:
+            t->kind = B200VA_K3_VEC256;
+            break;
+    }
+    t->ld_hint = LD_NA;
+    t->st_hint = ST_NA;
+    t->ctas_per_sm = 0;
+    if (n < (size_t{1} << 20)) {        // launch-bound: spread over as many SMs as possible
+        t->kind = B200VA_K1_VEC128;
+        t->threads = 128;
+        t->unroll = 1;
+    } else if (n < (size_t{1} << 24)) {
+        t->threads = 256;
+        t->unroll = 2;
+    } else {
+        t->threads = 512;
+        t->unroll = (t->kind == B200VA_K3_VEC256) ? 2 : 4;
+    }
+}
+
+inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+int check_args(const float* dA, const float* dB, const float* dC, size_t n)
+{
+    if (n == 0) return B200VA_OK;
+    if (!dA || !dB || !dC) return B200VA_ERR_INVALID;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dA), b = reinterpret_cast<uintptr_t>(dB),
+                    c = reinterpret_cast<uintptr_t>(dC);
+    if ((a | b | c) & 3u) return B200VA_ERR_ALIGN;
+    if (n > (size_t{1} << 40)) return B200VA_ERR_INVALID;
+    const uintptr_t bytes = n * sizeof(float);
+    auto partial = [&](uintptr_t x) { return x != c && x < c + bytes && c < x + bytes; };
+    if (partial(a) || partial(b)) return B200VA_ERR_OVERLAP;
+    return B200VA_OK;
+}
+
+int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t t, cudaStream_t stream)
+{
+    RC_TRY(check_args(dA, dB, dC, n));
+    const b200va_devinfo_t* di = nullptr;
+    RC_TRY(current_dev_info(&di));
+    if (n == 0) return B200VA_OK;
+
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dA), b = reinterpret_cast<uintptr_t>(dB),
+                    c = reinterpret_cast<uintptr_t>(dC);
+    const bool aliased = (a == c) || (b == c);
+    // .nc (non-coherent) loads require data that is read-only for the kernel's lifetime
+    if (aliased && t.ld_hint == LD_NC_NA) t.ld_hint = LD_PLAIN;
+
+    int vw = 0;
+    if (t.kind == B200VA_K3_VEC256) vw = 8;
+    else if (t.kind == B200VA_K1_VEC128 || t.kind == B200VA_K2_TMA) vw = 4;
+    else if (t.kind != B200VA_K0_SCALAR) return B200VA_ERR_VARIANT;
+
+    // vector body needs A, B, C equally misaligned w.r.t. the vector width
+    size_t head = 0;
+    while (vw) {
+        const uintptr_t mask = static_cast<uintptr_t>(vw) * 4u - 1u;
+        if ((a & mask) == (b & mask) && (a & mask) == (c & mask)) {
+            head = ((static_cast<uintptr_t>(vw) * 4u - (a & mask)) & mask) / 4u;
+            break;
+        }
+        if (t.kind == B200VA_K2_TMA) { vw = 0; break; }
+        vw = (vw == 8) ? 4 : 0;
+    }
+    if (vw == 0) {  // scalar control / mixed misalignment
+        const size_t blocks = (n + 255) / 256;
+        if (blocks > 0x7fffffffull) return B200VA_ERR_INVALID;
+        vadd_scalar<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(dA, dB, dC, n);
+        return cuda_err(cudaGetLastError());
+    }
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / static_cast<size_t>(vw);
+
+    if (t.kind == B200VA_K2_TMA) {
+        if (t.threads < 32 || t.threads > 992 || (t.threads & 31)) return B200VA_ERR_VARIANT;
+        if (t.stages < 2 || t.stages > 32) return B200VA_ERR_VARIANT;
+        if (t.tile_bytes < 2048 || (t.tile_bytes & 2047)) return B200VA_ERR_VARIANT;
+        if (t.st_hint < 0 || t.st_hint >= ST_HINTS) return B200VA_ERR_VARIANT;
+        const long long smem = static_cast<long long>(t.stages) * 2 * t.tile_bytes + 16LL * t.stages;
+        if (smem > di->max_smem_optin) return B200VA_ERR_VARIANT;
+        const bool hint = (t.ld_hint == LD_NA_EF);
+        tma_fn fn = pick_tma(t.store_mode, hint, t.st_hint);
+        if (!fn) return B200VA_ERR_VARIANT;
+        RC_TRY(ensure_smem_optin(fn, di->device, static_cast<int>(smem)));
+        const size_t ntiles = (nvec * 16u + t.tile_bytes - 1) / t.tile_bytes;
+        size_t grid = static_cast<size_t>(di->sm_count) * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1);
+        if (grid > ntiles) grid = ntiles;
+        if (grid == 0) grid = 1;
+        fn<<<static_cast<unsigned>(grid), t.threads + 32, static_cast<size_t>(smem), stream>>>(
+            dA, dB, dC, n, head, nvec, static_cast<uint32_t>(t.tile_bytes), static_cast<uint32_t>(t.stages));
+        return cuda_err(cudaGetLastError());
+    }
+
+    if (t.threads < 32 || t.threads > 1024 || (t.threads & 31)) return B200VA_ERR_VARIANT;
+    if (!is_pow2(t.unroll) || t.unroll > 8) return B200VA_ERR_VARIANT;
+    if (t.ld_hint < 0 || t.ld_hint >= LD_HINTS || t.st_hint < 0 || t.st_hint >= ST_HINTS)
+        return B200VA_ERR_VARIANT;
+    vec_fn fn = pick_vec(vw, t.unroll, t.ld_hint, t.st_hint);
+    if (!fn) return B200VA_ERR_VARIANT;
+    const size_t tile_vecs = static_cast<size_t>(t.threads) * t.unroll;
+    const size_t ntiles = (nvec + tile_vecs - 1) / tile_vecs;
+    size_t grid = ntiles;
+    if (t.ctas_per_sm > 0) {
+        const size_t cap = static_cast<size_t>(di->sm_count) * t.ctas_per_sm;
+        if (grid > cap) grid = cap;
+    }
+    if (grid > 0x7fffffffull) grid = 0x7fffffffull;   // kernel loops tile += gridDim.x
+    if (grid == 0) grid = 1;
+    fn<<<static_cast<unsigned>(grid), t.threads, 0, stream>>>(dA, dB, dC, n, head, nvec, ntiles);
+    return cuda_err(cudaGetLastError());
+}
+
+unsigned support_grid(const b200va_devinfo_t* di, size_t n, int threads)
+{
+    size_t want = (n + threads - 1) / threads;
+    size_t cap = static_cast<size_t>(di->sm_count) * 16;
+    if (want > cap) want = cap;
+    if (want == 0) want = 1;
+    return static_cast<unsigned>(want);
+}
+
+}  // namespace
+
+// =============================================================================== ABI
+extern "C" {
+
+int b200va_abi_version(void) { return B200VA_ABI_VERSION; }
+
+const char* b200va_strerror(int code)
+{
+    switch (code) {
+        case B200VA_OK:            return "success";
+        case B200VA_ERR_INVALID:   return "invalid argument";
+        case B200VA_ERR_ALIGN:     return "pointer not 4-byte aligned";
+        case B200VA_ERR_OVERLAP:   return "output partially overlaps an input";
+        case B200VA_ERR_VARIANT:   return "unknown kernel variant or unsupported geometry";
+        case B200VA_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+        case B200VA_ERR_VERIFY:    return "result verification failed";
+        case B200VA_ERR_NOMEM:     return "host allocation failed";
+    }
+    if (code <= B200VA_ERR_CUDA_BASE) return cudaGetErrorString(static_cast<cudaError_t>(-code - 1000));
+    return "unknown error";
+}
+
+int b200va_query(int device, b200va_devinfo_t* out)
+{
+    if (!out) return B200VA_ERR_INVALID;
+    const b200va_devinfo_t* di = nullptr;
+    const int rc = dev_info(device, &di);
+    if (di && (rc == B200VA_OK || rc == B200VA_ERR_NO_DEVICE) && di->sm_count > 0) *out = *di;
+    return rc;
+}
+
+int b200va_resolve(int variant, size_t n, b200va_tune_t* out)
+{
+    if (!out || variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
+    default_tune(variant, n, out);
+    return B200VA_OK;
+}
+
+int b200va_geometry(const b200va_tune_t* tune, size_t n, int device, unsigned* grid, unsigned* block,
+                    unsigned* dyn_smem_bytes)
+{
+    if (!tune || !grid || !block) return B200VA_ERR_INVALID;
+    const b200va_devinfo_t* di = nullptr;
+    RC_TRY(dev_info(device, &di));
+    b200va_tune_t t = *tune;
+    unsigned smem = 0;
+    if (t.kind == B200VA_K0_SCALAR) {
+        *grid = static_cast<unsigned>((n + 255) / 256);
+        *block = 256;
+    } else if (t.kind == B200VA_K2_TMA) {
+        const size_t nvec = n / 4;
+        const size_t ntiles = (nvec * 16u + t.tile_bytes - 1) / (t.tile_bytes ? t.tile_bytes : 1);
+        size_t g = static_cast<size_t>(di->sm_count) * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1);
+        if (g > ntiles) g = ntiles;
+        *grid = static_cast<unsigned>(g ? g : 1);
+        *block = static_cast<unsigned>(t.threads + 32);
+        smem = static_cast<unsigned>(t.stages * 2 * t.tile_bytes + 16 * t.stages);
+    } else if (t.kind == B200VA_K1_VEC128 || t.kind == B200VA_K3_VEC256) {
+        const size_t vw = t.kind == B200VA_K3_VEC256 ? 8 : 4;
+        const size_t tile_vecs = static_cast<size_t>(t.threads) * (t.unroll ? t.unroll : 1);
+        size_t g = (n / vw + tile_vecs - 1) / (tile_vecs ? tile_vecs : 1);
+        if (t.ctas_per_sm > 0 && g > static_cast<size_t>(di->sm_count) * t.ctas_per_sm)
+            g = static_cast<size_t>(di->sm_count) * t.ctas_per_sm;
+        if (g > 0x7fffffffull) g = 0x7fffffffull;
+        *grid = static_cast<unsigned>(g ? g : 1);
+        *block = static_cast<unsigned>(t.threads);
+    } else {
+        return B200VA_ERR_VARIANT;
+    }
+    if (dyn_smem_bytes) *dyn_smem_bytes = smem;
+    return B200VA_OK;
+}
+
+int b200va_add_f32(const float* dA, const float* dB, float* dC, size_t n, int variant, void* stream)
+{
+    if (variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
+    b200va_tune_t t;
+    default_tune(variant, n, &t);
+    return launch(dA, dB, dC, n, t, static_cast<cudaStream_t>(stream));
+}
+
+int b200va_add_f32_tuned(const float* dA, const float* dB, float* dC, size_t n,
+                         const b200va_tune_t* tune, void* stream)
+{
+    if (!tune) return B200VA_ERR_INVALID;
+    b200va_tune_t t = *tune;
+    b200va_tune_t d;
+    default_tune(t.kind, n, &d);
+    if (t.kind == B200VA_K_AUTO) t = d;
+    if (t.threads == 0) t.threads = d.threads;
+    if (t.unroll == 0) t.unroll = d.unroll ? d.unroll : 1;
+    if (t.stages == 0) t.stages = d.stages;
+    if (t.tile_bytes == 0) t.tile_bytes = d.tile_bytes;
+    return launch(dA, dB, dC, n, t, static_cast<cudaStream_t>(stream));
+}
+
+int b200va_add_f32_loop(const float* dA, const float* dB, float* dC, size_t n, int variant,
+                        int iters, int graph_batch, void* stream)
+{
+    if (iters < 0 || graph_batch < 0) return B200VA_ERR_INVALID;
+    if (variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    b200va_tune_t t;
+    default_tune(variant, n, &t);
+    if (graph_batch <= 1 || iters < graph_batch) {
+        for (int i = 0; i < iters; ++i) RC_TRY(launch(dA, dB, dC, n, t, st));
+        return B200VA_OK;
+    }
+    if (st == nullptr || st == cudaStreamLegacy) return B200VA_ERR_INVALID;  // not capturable
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CU_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = B200VA_OK;
+    for (int i = 0; i < graph_batch && rc == B200VA_OK; ++i) rc = launch(dA, dB, dC, n, t, st);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != B200VA_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    CU_TRY(e);
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return cuda_err(e); }
+    const int reps = iters / graph_batch, rest = iters % graph_batch;
+    for (int r = 0; r < reps && e == cudaSuccess; ++r) e = cudaGraphLaunch(exec, st);
+    for (int i = 0; i < rest && e == cudaSuccess && rc == B200VA_OK; ++i) rc = launch(dA, dB, dC, n, t, st);
+    // the executable graph must outlive its launches: graph mode drains the stream
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (rc != B200VA_OK) return rc;
+    CU_TRY(e);
+    CU_TRY(e2);
+    return B200VA_OK;
+}
+
+// ------------------------------------------------------------------ a2: input recipes
+int b200va_host_fill_rand_f32(float* hA, float* hB, size_t n)
+{
+    if (n && (!hA || !hB)) return B200VA_ERR_INVALID;
+    srand(1);  // a fresh ./vectorAdd process never calls srand: glibc default seed is 1
+    for (size_t i = 0; i < n; ++i) {
+        hA[i] = rand() / (float)RAND_MAX;
+        hB[i] = rand() / (float)RAND_MAX;
+    }
+    return B200VA_OK;
+}
+
+static inline uint64_t host_splitmix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+int b200va_host_fill_ctr_f32(float* h, size_t n, uint64_t seed, uint64_t first)
+{
+    if (n && !h) return B200VA_ERR_INVALID;
+    const uint64_t base = seed * 0x9E3779B97F4A7C15ull + first;
+    for (size_t i = 0; i < n; ++i)
+        h[i] = static_cast<float>(static_cast<uint32_t>(host_splitmix64(base + i) >> 40)) * 0x1.0p-24f;
+    return B200VA_OK;
+}
+
+int b200va_fill_ctr_f32(float* d, size_t n, uint64_t seed, uint64_t first, void* stream)
+{
+    if (n && !d) return B200VA_ERR_INVALID;
+    const b200va_devinfo_t* di = nullptr;
+    RC_TRY(current_dev_info(&di));
+    if (n == 0) return B200VA_OK;
+    fill_ctr<<<support_grid(di, n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d, n, seed * 0x9E3779B97F4A7C15ull + first);
+    return cuda_err(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ a6: verification
+int b200va_host_verify_f32(const float* hA, const float* hB, const float* hC, size_t n, size_t* first_bad)
+{
+    if (n && (!hA || !hB || !hC)) return B200VA_ERR_INVALID;
+    for (size_t i = 0; i < n; ++i) {
+        const float want = hA[i] + hB[i];
+        uint32_t uw, ug;
+        std::memcpy(&uw, &want, 4);
+        std::memcpy(&ug, &hC[i], 4);
+        if (uw == ug) continue;
+        const bool nw = (uw & 0x7fffffffu) > 0x7f800000u, ng = (ug & 0x7fffffffu) > 0x7f800000u;
+        if (nw && ng) continue;
+        if (first_bad) *first_bad = i;
+        return B200VA_ERR_VERIFY;
+    }
+    return B200VA_OK;
+}
+
+int b200va_verify_f32(const float* dA, const float* dB, const float* dC, size_t n,
+                      uint64_t* d_result, void* stream)
+{
+    if (!d_result || (n && (!dA || !dB || !dC))) return B200VA_ERR_INVALID;
+    const b200va_devinfo_t* di = nullptr;
+    RC_TRY(current_dev_info(&di));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto* res = reinterpret_cast<unsigned long long*>(d_result);
+    reset_verify<<<1, 1, 0, st>>>(res);
+    if (n) verify_bits<<<support_grid(di, n, 256), 256, 0, st>>>(dA, dB, dC, n, res);
+    return cuda_err(cudaGetLastError());
+}
+
+int b200va_digest_f32(const float* d, size_t n, uint64_t* d_out, void* stream)
+{
+    if (!d_out || (n && !d)) return B200VA_ERR_INVALID;
+    const b200va_devinfo_t* di = nullptr;
+    RC_TRY(current_dev_info(&di));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto* out = reinterpret_cast<unsigned long long*>(d_out);
+    reset_digest<<<1, 1, 0, st>>>(out);
+    if (n) digest_bits<<<support_grid(di, n, 256), 256, 0, st>>>(d, n, out);
+    return cuda_err(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ shard arithmetic
+int b200va_shard_range(size_t n, int world, int rank, size_t* begin, size_t* end)
+{
+    if (world < 1 || rank < 0 || rank >= world || !begin || !end) return B200VA_ERR_INVALID;
+    size_t chunk = (n + static_cast<size_t>(world) - 1) / static_cast<size_t>(world);
+    chunk = (chunk + 7) & ~size_t{7};  // shard starts stay 32-byte aligned (256-bit body)
+    size_t b = static_cast<size_t>(rank) * chunk;
+    if (b > n) b = n;
+    size_t e = b + chunk;
+    if (e > n) e = n;
+    *begin = b;
+    *end = e;
+    return B200VA_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer path
+struct b200va_stager {
+    int device = 0;
+    size_t chunk = 0;
+    int depth = 0;
+    float* d_buf = nullptr;            // depth * 3 * chunk floats
+    cudaStream_t main = nullptr;
+    cudaStream_t* slot = nullptr;
+    cudaEvent_t* slot_done = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    float last_ms = 0.f;
+};
+
+int b200va_host_alloc(void** out, size_t bytes)
+{
+    if (!out) return B200VA_ERR_INVALID;
+    CU_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+    return B200VA_OK;
+}
+
+int b200va_host_free(void* p)
+{
+    if (!p) return B200VA_OK;
+    CU_TRY(cudaFreeHost(p));
+    return B200VA_OK;
+}
+
+int b200va_stager_destroy(b200va_stager_t* s)
+{
+    if (!s) return B200VA_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    if (s->slot) {
+        for (int i = 0; i < s->depth; ++i) {
+            if (s->slot[i]) cudaStreamDestroy(s->slot[i]);
+            if (s->slot_done && s->slot_done[i]) cudaEventDestroy(s->slot_done[i]);
+        }
+    }
+    if (s->main) cudaStreamDestroy(s->main);
+    if (s->ev_start) cudaEventDestroy(s->ev_start);
+    if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+    if (s->d_buf) cudaFree(s->d_buf);
+    delete[] s->slot;
+    delete[] s->slot_done;
+    delete s;
+    if (prev >= 0) cudaSetDevice(prev);
+    return B200VA_OK;
+}
+
+int b200va_stager_create(b200va_stager_t** out, int device, size_t chunk_elems, int depth)
+{
+    if (!out) return B200VA_ERR_INVALID;
+    *out = nullptr;
+    if (chunk_elems == 0) chunk_elems = size_t{1} << 22;   // 16 MiB per array per slot
+    if (depth == 0) depth = 3;
+    if (depth < 1 || depth > 16) return B200VA_ERR_INVALID;
+    chunk_elems = (chunk_elems + 63) & ~size_t{63};        // slots stay 256-B aligned
+    RC_TRY(dev_info(device, nullptr));
+    CU_TRY(cudaSetDevice(device));
+    b200va_stager* s = new (std::nothrow) b200va_stager;
+    if (!s) return B200VA_ERR_NOMEM;
+    s->device = device;
+    s->chunk = chunk_elems;
+    s->depth = depth;
+    s->slot = new (std::nothrow) cudaStream_t[depth]();
+    s->slot_done = new (std::nothrow) cudaEvent_t[depth]();
+    if (!s->slot || !s->slot_done) { b200va_stager_destroy(s); return B200VA_ERR_NOMEM; }
+    cudaError_t e = cudaMalloc(&s->d_buf, static_cast<size_t>(depth) * 3 * chunk_elems * sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->main, cudaStreamNonBlocking);
+    for (int i = 0; i < depth && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&s->slot[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->slot_done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_stop);
+    if (e != cudaSuccess) { b200va_stager_destroy(s); return cuda_err(e); }
+    *out = s;
+    return B200VA_OK;
+}
+
+int b200va_stager_add_f32(b200va_stager_t* s, const float* hA, const float* hB, float* hC, size_t n,
+                          int variant, int mode)
+{
+    if (!s || (n && (!hA || !hB || !hC))) return B200VA_ERR_INVALID;
+    if (variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaEventRecord(s->ev_start, s->main));
+    if (mode == 1) {
+        // zero-copy: the kernel streams A and B from pinned host memory over PCIe and
+        // writes C back the same way -- both link directions busy, no staging latency.
+        const float *dA = nullptr, *dB = nullptr;
+        float* dC = nullptr;
+        if (n) {
+            CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(const_cast<float**>(&dA)),
+                                            const_cast<float*>(hA), 0));
+            CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(const_cast<float**>(&dB)),
+                                            const_cast<float*>(hB), 0));
+            CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dC), hC, 0));
+        }
+        b200va_tune_t t;
+        default_tune(variant == B200VA_K_AUTO ? B200VA_K1_VEC128 : variant, n, &t);
+        RC_TRY(launch(dA, dB, dC, n, t, s->main));
+    } else if (mode == 0) {
+        const size_t nchunks = (n + s->chunk - 1) / s->chunk;
+        for (int i = 0; i < s->depth; ++i) CU_TRY(cudaStreamWaitEvent(s->slot[i], s->ev_start, 0));
+        b200va_tune_t t;
+        for (size_t k = 0; k < nchunks; ++k) {
+            const int i = static_cast<int>(k % static_cast<size_t>(s->depth));
+            const size_t off = k * s->chunk;
+            const size_t m = (n - off < s->chunk) ? n - off : s->chunk;
+            float* dA = s->d_buf + static_cast<size_t>(i) * 3 * s->chunk;
+            float* dB = dA + s->chunk;
+            float* dC = dB + s->chunk;
+            CU_TRY(cudaMemcpyAsync(dA, hA + off, m * sizeof(float), cudaMemcpyHostToDevice, s->slot[i]));
+            CU_TRY(cudaMemcpyAsync(dB, hB + off, m * sizeof(float), cudaMemcpyHostToDevice, s->slot[i]));
+            default_tune(variant, m, &t);
+            RC_TRY(launch(dA, dB, dC, m, t, s->slot[i]));
+            CU_TRY(cudaMemcpyAsync(hC + off, dC, m * sizeof(float), cudaMemcpyDeviceToHost, s->slot[i]));
+        }
+        for (int i = 0; i < s->depth; ++i) {
+            CU_TRY(cudaEventRecord(s->slot_done[i], s->slot[i]));
+            CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[i], 0));
+        }
+    } else {
+        return B200VA_ERR_INVALID;
+    }
+    CU_TRY(cudaEventRecord(s->ev_stop, s->main));
+    CU_TRY(cudaStreamSynchronize(s->main));
+    CU_TRY(cudaEventElapsedTime(&s->last_ms, s->ev_start, s->ev_stop));
+    return B200VA_OK;
+}
+
+int b200va_stager_last_ms(b200va_stager_t* s, float* ms)
+{
+    if (!s || !ms) return B200VA_ERR_INVALID;
+    *ms = s->last_ms;
+    return B200VA_OK;
+}
+
+int b200va_add_f32_host(const float* hA, const float* hB, float* hC, size_t n, int device, int variant)
+{
+    b200va_stager_t* s = nullptr;
+    size_t chunk = size_t{1} << 22;
+    if (n < chunk) chunk = n ? n : 1;
+    RC_TRY(b200va_stager_create(&s, device, chunk, n > chunk ? 3 : 1));
+    const int rc = b200va_stager_add_f32(s, hA, hB, hC, n, variant, 0);
+    b200va_stager_destroy(s);
+    return rc;
+}
+
+}  // extern "C"

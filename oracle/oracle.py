@@ -1,0 +1,148 @@
+"""ctypes wrapper over oracle/liboracle_vadd.so (built by oracle/Makefile)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle_vadd.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "vadd_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    return LIB_PATH
+
+
+if not os.path.exists(LIB_PATH):
+    build()
+_lib = C.CDLL(LIB_PATH)
+_P, _SZ, _U64, _I = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int
+for _n, _r, _a in [
+    ("oracle_vadd_f32", None, [_P, _P, _P, _SZ]),
+    ("oracle_softfloat_add_f32", C.c_uint32, [C.c_uint32, C.c_uint32]),
+    ("oracle_softfloat_vadd_f32", None, [_P, _P, _P, _SZ]),
+    ("oracle_fill_rand_f32", None, [_P, _P, _SZ]),
+    ("oracle_fill_ctr_f32", None, [_P, _SZ, _U64, _U64]),
+    ("oracle_verify_sample_tolerance", C.c_longlong, [_P, _P, _P, _SZ]),
+    ("oracle_first_mismatch_f32", C.c_longlong, [_P, _P, _SZ]),
+    ("oracle_fnv1a64", _U64, [_P, _SZ]),
+    ("oracle_bits_digest_u32", None, [_P, _SZ, _P]),
+    ("oracle_vadd_digest_f32", None, [_P, _P, _SZ, _P]),
+    ("oracle_num_cpus", _I, []),
+    ("oracle_vadd_f32_mt", None, [_P, _P, _P, _SZ, _I]),
+    ("oracle_fill_ctr_pair_mt", None, [_P, _P, _P, _SZ, _U64, _U64, _U64, _I]),
+    ("oracle_vadd_digest_f32_mt", None, [_P, _P, _SZ, _I, _P]),
+    ("oracle_time_vadd_mt", _I, [_SZ, _I, _I, _I, _P]),
+]:
+    _f = getattr(_lib, _n)
+    _f.restype, _f.argtypes = _r, _a
+
+SEED_A, SEED_B = 0x0A, 0x0B
+
+
+def _f32(x: np.ndarray) -> np.ndarray:
+    assert x.dtype == np.float32 and x.flags.c_contiguous
+    return x
+
+
+def vadd(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """C[i] = A[i] + B[i], scalar single-thread C loop (the reference kernel's arithmetic)."""
+    c = np.empty_like(_f32(a))
+    _lib.oracle_vadd_f32(a.ctypes.data, _f32(b).ctypes.data, c.ctypes.data, a.size)
+    return c
+
+
+def vadd_mt(a: np.ndarray, b: np.ndarray, threads: int = 0) -> np.ndarray:
+    c = np.empty_like(_f32(a))
+    _lib.oracle_vadd_f32_mt(a.ctypes.data, _f32(b).ctypes.data, c.ctypes.data, a.size, threads or num_cpus())
+    return c
+
+
+def softfloat_vadd_bits(ua: np.ndarray, ub: np.ndarray) -> np.ndarray:
+    assert ua.dtype == np.uint32 and ub.dtype == np.uint32
+    uc = np.empty_like(ua)
+    _lib.oracle_softfloat_vadd_f32(np.ascontiguousarray(ua).ctypes.data, np.ascontiguousarray(ub).ctypes.data,
+                                   uc.ctypes.data, ua.size)
+    return uc
+
+
+def softfloat_add_bits(ua: int, ub: int) -> int:
+    return int(_lib.oracle_softfloat_add_f32(ua, ub))
+
+
+def fill_rand(n: int) -> tuple[np.ndarray, np.ndarray]:
+    a, b = np.empty(n, np.float32), np.empty(n, np.float32)
+    _lib.oracle_fill_rand_f32(a.ctypes.data, b.ctypes.data, n)
+    return a, b
+
+
+def fill_ctr(n: int, seed: int, first: int = 0) -> np.ndarray:
+    x = np.empty(n, np.float32)
+    _lib.oracle_fill_ctr_f32(x.ctypes.data, n, seed, first)
+    return x
+
+
+def verify_sample_tolerance(a, b, c) -> int:
+    return int(_lib.oracle_verify_sample_tolerance(_f32(a).ctypes.data, _f32(b).ctypes.data, _f32(c).ctypes.data, a.size))
+
+
+def first_mismatch(x: np.ndarray, y: np.ndarray) -> int:
+    assert x.size == y.size
+    return int(_lib.oracle_first_mismatch_f32(_f32(x).ctypes.data, _f32(y).ctypes.data, x.size))
+
+
+def fnv1a64(x: np.ndarray) -> int:
+    x = np.ascontiguousarray(x)
+    return int(_lib.oracle_fnv1a64(x.ctypes.data, x.nbytes))
+
+
+def bits_digest(x: np.ndarray) -> tuple[int, int]:
+    out = (C.c_uint64 * 2)()
+    _lib.oracle_bits_digest_u32(_f32(x).ctypes.data, x.size, out)
+    return int(out[0]), int(out[1])
+
+
+def vadd_digest(a: np.ndarray, b: np.ndarray, threads: int = 1) -> tuple[int, int]:
+    out = (C.c_uint64 * 2)()
+    if threads > 1:
+        _lib.oracle_vadd_digest_f32_mt(_f32(a).ctypes.data, _f32(b).ctypes.data, a.size, threads, out)
+    else:
+        _lib.oracle_vadd_digest_f32(_f32(a).ctypes.data, _f32(b).ctypes.data, a.size, out)
+    return int(out[0]), int(out[1])
+
+
+def ctr_vadd_digest(n: int, first: int = 0, threads: int = 0, block: int = 1 << 24) -> tuple[int, int]:
+    """Digest of ctr(A)+ctr(B) over [first, first+n) without holding the vectors: the
+    full-size (2^28 / 2^30) checker."""
+    threads = threads or num_cpus()
+    s, x = 0, 0
+    a = np.empty(min(block, max(n, 1)), np.float32)
+    b = np.empty_like(a)
+    done = 0
+    while done < n:
+        m = min(block, n - done)
+        _lib.oracle_fill_ctr_pair_mt(a.ctypes.data, b.ctypes.data, None, m, SEED_A, SEED_B, first + done, threads)
+        out = (C.c_uint64 * 2)()
+        _lib.oracle_vadd_digest_f32_mt(a.ctypes.data, b.ctypes.data, m, threads, out)
+        s = (s + int(out[0])) & 0xFFFFFFFFFFFFFFFF
+        x ^= int(out[1])
+        done += m
+    return s, x
+
+
+def num_cpus() -> int:
+    return int(_lib.oracle_num_cpus())
+
+
+def time_vadd_mt(n: int, threads: int = 0, warmup: int = 1, reps: int = 5) -> list[float]:
+    """Per-pass seconds of the all-cores add over n elements (buffers first-touched by the workers)."""
+    secs = (C.c_double * reps)()
+    rc = _lib.oracle_time_vadd_mt(n, threads or num_cpus(), warmup, reps, secs)
+    if rc != 0:
+        raise MemoryError("oracle_time_vadd_mt: allocation failed")
+    return list(secs)
