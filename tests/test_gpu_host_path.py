@@ -1,0 +1,88 @@
+"""The host-buffer path (a3 + a4 + a6-copy of one ./vectorAdd process) and the drop-in
+executable, on a real GPU, against the oracle."""
+import json
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import has_gpu
+
+pytestmark = pytest.mark.gpu
+if has_gpu():
+    import torch
+
+    from k8s_gpu_hpa_b200 import capi, vector_add as va
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 50000, (1 << 22) + 3, 3 * (1 << 22) + 17])
+def test_add_host_pageable_arrays(n):
+    ha, hb = oracle.fill_ctr(n, 0x0A, 3), oracle.fill_ctr(n, 0x0B, 3)
+    out = va.add_host(ha, hb)
+    assert oracle.first_mismatch(out, oracle.vadd(ha, hb)) == -1
+
+
+@pytest.mark.parametrize("zero_copy", [False, True])
+@pytest.mark.parametrize("chunk,depth", [(1 << 16, 2), (1 << 20, 3), (0, 0)])
+def test_stager_pinned_pipeline(zero_copy, chunk, depth):
+    n = 5_000_011
+    ha = torch.from_numpy(oracle.fill_ctr(n, 0x0A, 1)).pin_memory()
+    hb = torch.from_numpy(oracle.fill_ctr(n, 0x0B, 1)).pin_memory()
+    hc = torch.full((n,), -1.0).pin_memory()
+    want = oracle.vadd(ha.numpy(), hb.numpy())
+    with va.Stager(0, chunk, depth) as st:
+        for m in (n, n - 3, 1 << 16, 7):
+            hc.fill_(-1.0)
+            ms = st.add(ha[:m], hb[:m], hc[:m], zero_copy=zero_copy)
+            assert ms > 0
+            assert oracle.first_mismatch(hc[:m].numpy(), want[:m]) == -1
+            assert bool((hc[m:] == -1.0).all())
+
+
+def test_cli_zero_arguments_is_the_reference_process():
+    """`./vectorAdd` exactly as cuda-test-deployment.yaml:19 runs it."""
+    p = va.run_cli()
+    assert p.returncode == 0, p.stderr
+    lines = p.stdout.strip().splitlines()
+    assert lines[0] == "[Vector addition of 50000 elements]"
+    assert lines[1] == "Copy input data from the host memory to the CUDA device"
+    assert lines[2].startswith("CUDA kernel launch with ") and lines[2].endswith(" threads")
+    assert lines[3] == "Copy output data from the CUDA device to the host memory"
+    assert lines[4] == "Test PASSED" and lines[5] == "Done"
+
+
+def test_cli_bash_launch_loop_shape():
+    """The Deployment's bash loop, shortened: every iteration a fresh process, exit status ignored."""
+    import subprocess
+
+    p = subprocess.run(["bash", "-c", "for (( c=1; c<=3; c++ )); do ./vectorAdd; done"],
+                       cwd=capi._HERE, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.count("Test PASSED") == 3
+
+
+@pytest.mark.parametrize("kernel", ["auto", "k0", "k1", "k2", "k3"])
+def test_cli_sample_mode_options(kernel):
+    p = va.run_cli("--n", "1000003", "--iters", "5", "--kernel", kernel)
+    assert p.returncode == 0 and "Test PASSED" in p.stdout, p.stderr
+    p = va.run_cli("--n", "2^20", "--gen", "ctr", "--iters", "12", "--graph", "4", "--kernel", kernel)
+    assert p.returncode == 0 and "Test PASSED" in p.stdout, p.stderr
+
+
+def test_cli_resident_mode_reports_oracle_digest():
+    n = (1 << 24) + 40
+    p = va.run_cli("--mode", "resident", "--n", str(n), "--iters", "20")
+    assert p.returncode == 0, p.stderr
+    r = json.loads(p.stdout.strip().splitlines()[-1])
+    s, x = oracle.ctr_vadd_digest(n)
+    assert r["mismatches"] == 0 and int(r["digest_sum"], 16) == s and int(r["digest_xor"], 16) == x
+    assert r["launches_per_gpu"] == 20 and r["elements_per_s"] > 1e9
+
+
+def test_cli_staged_mode_and_duty_cycle():
+    p = va.run_cli("--mode", "staged", "--n", str((1 << 23) + 1), "--iters", "2")
+    assert p.returncode == 0, p.stderr
+    assert json.loads(p.stdout.strip().splitlines()[-1])["mismatches"] == 0
+    p = va.run_cli("--n", "2^22", "--iters", "50", "--duration", "1.0", "--target-util", "30", "--nvml")
+    assert p.returncode == 0, p.stderr
+    r = json.loads(p.stdout.strip().splitlines()[-1])
+    assert r["mismatches"] == 0 and 0.0 < r["gpu_busy_frac"] < 0.9

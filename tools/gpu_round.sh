@@ -1,0 +1,75 @@
+#!/usr/bin/env bash
+# One batched GPU session (gpurun boxes are expensive to get): smoke, sweep, tests, bench, ncu.
+# Usage (from the repo root on the GPU box):  bash tools/gpu_round.sh <tag> [stages...]
+# Everything lands in gpurun_out/<tag>/ ; each stage is wrapped in `timeout`.
+set -u
+TAG=${1:-r01}; shift || true
+STAGES=${*:-"info smoke sweep tests bench ncu"}
+OUT=gpurun_out/$TAG
+PKG=k8s-gpu-hpa_b200
+mkdir -p "$OUT"
+has() { [[ " $STAGES " == *" $1 "* ]]; }
+
+if has info; then
+  nvidia-smi > "$OUT/nvidia-smi.txt" 2>&1
+  nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit,memory.total --format=csv >> "$OUT/nvidia-smi.txt" 2>&1
+  nproc > "$OUT/host.txt"; lscpu | head -25 >> "$OUT/host.txt"; free -g >> "$OUT/host.txt"
+fi
+
+if has smoke; then
+  timeout 600 python __graft_entry__.py smoke > "$OUT/smoke.log" 2>&1; echo "smoke exit=$?" | tee -a "$OUT/status.txt"
+fi
+
+if has sweep; then
+  python tools/gen_geometries.py all > "$OUT/geometries.txt"
+  timeout 900 $PKG/b200va_tune --n $((1<<28)) --reps 20 --warmup 3 < "$OUT/geometries.txt" > "$OUT/tune_2p28.jsonl" 2> "$OUT/tune_2p28.err"
+  echo "sweep 2^28 exit=$?" | tee -a "$OUT/status.txt"
+  timeout 600 $PKG/b200va_tune --n $((1<<24)) --reps 50 --warmup 5 < "$OUT/geometries.txt" > "$OUT/tune_2p24.jsonl" 2> "$OUT/tune_2p24.err"
+  echo "sweep 2^24 exit=$?" | tee -a "$OUT/status.txt"
+fi
+
+if has tests; then
+  timeout 1500 python -m pytest tests -q -m gpu -x > "$OUT/pytest_gpu.log" 2>&1; echo "pytest gpu exit=$?" | tee -a "$OUT/status.txt"
+  tail -5 "$OUT/pytest_gpu.log"
+fi
+
+if has bench; then
+  nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap \
+      --format=csv -lms 200 > "$OUT/clocks.csv" &
+  SMI=$!
+  timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > "$OUT/bench_reference.json" 2> "$OUT/bench_reference.err"; echo "bench reference exit=$?" | tee -a "$OUT/status.txt"
+  timeout 900 python bench.py > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench exit=$?" | tee -a "$OUT/status.txt"
+  for k in k0 k1 k2 k3; do
+    timeout 600 python bench.py --kernel $k --steps 100 --no-e2e --no-cpu-baseline > "$OUT/bench_$k.json" 2>> "$OUT/bench.err"
+  done
+  timeout 600 python bench.py --zero-copy --steps 20 --no-cpu-baseline > "$OUT/bench_zero_copy.json" 2>> "$OUT/bench.err"
+  kill $SMI
+  cat "$OUT/bench.json"
+fi
+
+if has cli; then
+  ( cd $PKG
+    timeout 300 ./vectorAdd > "../$OUT/cli_default.log" 2>&1; echo "cli default exit=$?" | tee -a "../$OUT/status.txt"
+    timeout 600 ./vectorAdd --mode resident --n 2^28 --iters 100 --cpu-baseline --json "../$OUT/cli_2p28.json" > /dev/null 2>> "../$OUT/cli.err"
+    timeout 600 ./vectorAdd --mode resident --n 2^24 --iters 5000 --nvml --duration 20 --json "../$OUT/cli_hpa_replay.json" > /dev/null 2>> "../$OUT/cli.err"
+    timeout 600 ./vectorAdd --mode resident --n 2^24 --iters 5000 --graph 100 --json "../$OUT/cli_loop_graph.json" > /dev/null 2>> "../$OUT/cli.err"
+    timeout 600 ./vectorAdd --mode staged --n 2^28 --iters 5 --json "../$OUT/cli_staged.json" > /dev/null 2>> "../$OUT/cli.err"
+  )
+fi
+
+if has ncu; then
+  # launch list of the bench command (cold-cache, serialised: compare shares, not absolutes)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
+      python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > "$OUT/ncu_launches.log" 2>&1
+  echo "ncu launches exit=$?" | tee -a "$OUT/status.txt"
+  # full capture of the production kernel and of the variants
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:vadd_ -s 3 -c 2 -f -o "$OUT/prof_auto" \
+      python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1
+  echo "ncu full exit=$?" | tee -a "$OUT/status.txt"
+  for k in k0 k1 k2; do
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:vadd_ -s 3 -c 1 -f -o "$OUT/prof_$k" \
+        $PKG/vectorAdd --mode resident --n 2^28 --iters 3 --kernel $k --verify none >> "$OUT/ncu_full.log" 2>&1
+  done
+fi
+ls -la "$OUT" | head -50
+cat "$OUT/status.txt"
