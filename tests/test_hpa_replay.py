@@ -1,0 +1,51 @@
+"""The control-loop arithmetic of the (unchanged) manifests, restated offline."""
+import os
+
+import pytest
+
+from conftest import ROOT
+from k8s_gpu_hpa_b200 import hpa_replay as hr
+
+
+def test_constants_match_the_reference_manifests_when_present():
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present on this machine")
+    hpa = open(os.path.join(ref, "cuda-test-hpa.yaml")).read()
+    assert f"targetValue: {int(hr.HPA_TARGET)}" in hpa
+    assert f"minReplicas: {hr.HPA_MIN}" in hpa and f"maxReplicas: {hr.HPA_MAX}" in hpa
+    assert f'"-c", "{int(hr.DCGM_INTERVAL_S * 1000)}"' in open(os.path.join(ref, "dcgm-exporter.yaml")).read().replace("'", '"') \
+        or "10000" in open(os.path.join(ref, "dcgm-exporter.yaml")).read()
+    assert "scrape_interval: 1s" in open(os.path.join(ref, "kube-prometheus-stack-values.yaml")).read()
+
+
+def test_recording_rule_max_by_pod_then_avg_over_labelled_pods():
+    S = hr.Sample
+    dcgm = [S("n0", "cuda-test-a", "default", 12.0, "0"), S("n0", "cuda-test-a", "default", 30.0, "1"),   # 2 GPUs, one pod
+            S("n1", "cuda-test-b", "default", 10.0), S("n1", "other-pod", "default", 99.0)]
+    labels = {"cuda-test-a": "cuda-test", "cuda-test-b": "cuda-test", "other-pod": "something-else"}
+    assert hr.cuda_test_gpu_avg(dcgm, labels) == pytest.approx((30.0 + 10.0) / 2)
+    assert hr.cuda_test_gpu_avg([S("n1", "other-pod", "default", 99.0)], labels) is None
+
+
+@pytest.mark.parametrize("current,metric,want", [
+    (1, 4.0, 1), (1, 5.0, 1), (1, 5.4, 1),       # inside the 10 % tolerance band
+    (1, 5.6, 2), (1, 9.9, 2), (1, 10.1, 3), (1, 99.0, 3),
+    (2, 5.6, 3), (3, 50.0, 3),                   # maxReplicas clamp
+    (3, 1.0, 1), (2, 2.4, 1), (3, 3.0, 2),       # scale-down ("if the usage drops low enough")
+    (1, None, 1), (1, 0.0, 1),
+])
+def test_hpa_decision(current, metric, want):
+    assert hr.hpa_desired_replicas(current, metric) == want
+
+
+def test_replay_reference_shape_vs_sustained_loop():
+    # the reference's duty cycle (process churn) sits under the threshold; a sustained
+    # in-process loop crosses it and the overshoot the README warns about appears
+    idle = {"cuda-test-0": [(t, 3.0) for t in range(0, 120)]}
+    r = hr.Replay()
+    assert all(rep == 1 for _, _, rep in r.run(idle, 120))
+    busy = {f"cuda-test-{i}": [(t, 97.0) for t in range(0, 120)] for i in range(3)}
+    ev = r.run(busy, 120)
+    assert ev[0][2] == 3 or ev[1][2] == 3                       # jumps straight to maxReplicas
+    assert hr.would_scale_up(6.0) and not hr.would_scale_up(5.2)

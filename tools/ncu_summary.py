@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Summarise .ncu-rep captures (read here, no GPU needed) into JSON + markdown for profiles/.
+
+    python tools/ncu_summary.py gpurun_out/r01/prof_auto.ncu-rep [more.ncu-rep ...] --out profiles/r01
+"""
+import argparse
+import csv
+import io
+import json
+import os
+import subprocess
+
+KEEP = {
+    "gpu__time_duration.sum": "duration_ns",
+    "dram__bytes_read.sum": "dram_read_bytes",
+    "dram__bytes_write.sum": "dram_write_bytes",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "gpu_dram_pct_of_peak",
+    "dram__cycles_active.avg.pct_of_peak_sustained_elapsed": "dram_cycles_active_pct",
+    "lts__t_sector_hit_rate.pct": "l2_hit_rate_pct",
+    "lts__t_bytes.sum": "l2_bytes",
+    "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
+    "launch__registers_per_thread": "registers_per_thread",
+    "launch__grid_size": "grid",
+    "launch__block_size": "block",
+    "launch__shared_mem_per_block_dynamic": "dyn_smem_bytes",
+    "launch__occupancy_limit_registers": "occ_limit_regs",
+    "launch__occupancy_limit_shared_mem": "occ_limit_smem",
+    "launch__occupancy_limit_warps": "occ_limit_warps",
+    "launch__waves_per_multiprocessor": "waves_per_sm",
+    "sm__cycles_elapsed.avg.per_second": "sm_clock_hz",
+    "dram__cycles_elapsed.avg.per_second": "dram_clock_hz",
+    "smsp__inst_executed.sum": "warp_insts",
+    "l1tex__t_bytes.sum": "l1tex_bytes",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio": "stall_long_scoreboard",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard",
+}
+
+
+def read_raw(rep: str):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    header, units, data = rows[0], rows[1], rows[2:]
+    res = []
+    for r in data:
+        d = {"kernel": r[header.index("Kernel Name")], "id": r[header.index("ID")]}
+        for col, unit, val in zip(header, units, r):
+            if col in KEEP:
+                try:
+                    v = float(val.replace(",", ""))
+                except ValueError:
+                    continue
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "usecond": 1e3, "msecond": 1e6, "nsecond": 1,
+                         "second": 1e9, "Ghz": 1e9, "Mhz": 1e6, "hz": 1}.get(unit, 1)
+                if KEEP[col].endswith(("_bytes", "_ns", "_hz")):
+                    v *= scale
+                d[KEEP[col]] = v
+        if "dram_read_bytes" in d and "dram_write_bytes" in d:
+            d["dram_bytes"] = d["dram_read_bytes"] + d["dram_write_bytes"]
+            if d.get("duration_ns"):
+                d["dram_GBps"] = d["dram_bytes"] / d["duration_ns"]
+        res.append(d)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("reps", nargs="+")
+    ap.add_argument("--out", required=True, help="output prefix (writes <out>_ncu.json and <out>_ncu.md)")
+    ap.add_argument("--n", type=int, default=1 << 28)
+    args = ap.parse_args()
+    allk = []
+    for rep in args.reps:
+        for d in read_raw(rep):
+            d["report"] = os.path.basename(rep)
+            d["algorithmic_bytes"] = 12 * args.n
+            if d.get("duration_ns"):
+                d["algorithmic_GBps"] = d["algorithmic_bytes"] / d["duration_ns"]
+            if d.get("dram_bytes"):
+                d["traffic_over_algorithmic"] = d["dram_bytes"] / d["algorithmic_bytes"]
+            allk.append(d)
+    json.dump(allk, open(args.out + "_ncu.json", "w"), indent=1)
+    cols = ["report", "kernel", "grid", "block", "registers_per_thread", "dyn_smem_bytes", "duration_ns", "algorithmic_GBps",
+            "dram_GBps", "dram_bytes", "traffic_over_algorithmic", "dram_pct_of_peak", "l2_hit_rate_pct",
+            "achieved_occupancy_pct", "sm_clock_hz"]
+    with open(args.out + "_ncu.md", "w") as f:
+        f.write("| " + " | ".join(cols) + " |\n|" + "---|" * len(cols) + "\n")
+        for d in allk:
+            def fmt(c):
+                v = d.get(c, "")
+                if isinstance(v, float):
+                    return f"{v:.4g}" if abs(v) < 1e6 else f"{v:.6g}"
+                return str(v)[:60]
+            f.write("| " + " | ".join(fmt(c) for c in cols) + " |\n")
+    print(open(args.out + "_ncu.md").read())
+
+
+if __name__ == "__main__":
+    main()
