@@ -128,14 +128,15 @@ def run_reference(args) -> None:
         return
     import oracle
 
-    threads = oracle.num_cpus()
+    threads, rates = oracle.best_thread_count()   # all the host threads the add can use (quota-aware)
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     steps = min(steps, 50)  # 2^28 elements per pass on host cores: keep the run within minutes
     secs = cpu_time_passes(N_PER_GPU, threads, warmup, steps)
     total = sum(secs)
     value = N_PER_GPU * steps / total
     sample = (f"{steps} passes of C=A+B over 2^28 fp32 elements (one GPU's shard of the workload), "
-              f"{threads} host threads, contiguous static partition, regular stores")
+              f"{threads} host threads (fastest of {sorted(rates)} tried; {oracle.num_cpus()} CPUs in the affinity mask, "
+              f"cgroup quota {oracle.cpu_quota() or 'none'}), contiguous static partition, regular stores")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
@@ -209,9 +210,10 @@ def run_ours(args) -> None:
     # ---- e2e: host buffers through the C ABI, H2D + add + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        ha = torch.empty(n, dtype=torch.float32, pin_memory=True)
-        hb = torch.empty(n, dtype=torch.float32, pin_memory=True)
-        hc = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        # pinned host buffers from the C ABI (pages on the GPU's NUMA node), filled from the
+        # device arrays outside the timed region
+        pa, pb, pc = va.PinnedBuffer(n), va.PinnedBuffer(n), va.PinnedBuffer(n)
+        ha, hb, hc = (torch.from_numpy(p.array) for p in (pa, pb, pc))
         ha.copy_(a); hb.copy_(b)
         torch.cuda.synchronize()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -236,6 +238,8 @@ def run_ours(args) -> None:
                                                    "copy-engine pipeline: H2D(A,B) -> add -> D2H(C) per chunk"),
                "host_memory": "pinned"}
         del ha, hb, hc
+        for p in (pa, pb, pc):
+            p.free()
 
     if rank != 0:
         return
@@ -271,12 +275,14 @@ def run_ours(args) -> None:
     if ws == 1 and not args.no_cpu_baseline:
         import oracle
 
-        threads = oracle.num_cpus()
+        threads, rates = oracle.best_thread_count()
         secs = cpu_time_passes(n, threads, 1, 5)
         v = n * len(secs) / sum(secs)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "5 passes over the full 2^28-element workload, all host threads, "
-                                          "oracle/vadd_oracle.c (reference ships no source: port of its arithmetic)",
+                                "sample": f"5 passes over the full 2^28-element workload, {threads} host threads (fastest of "
+                                          f"{sorted(rates)} tried; affinity {oracle.num_cpus()} CPUs, cgroup quota "
+                                          f"{oracle.cpu_quota() or 'none'}), oracle/vadd_oracle.c (reference ships no source: "
+                                          "port of its arithmetic)",
                                 "algorithmic_GBps": v * BYTES_PER_ELEM / 1e9}
     print(json.dumps(line), flush=True)
 

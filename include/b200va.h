@@ -107,9 +107,20 @@ int b200va_add_f32_tuned(const float *dA, const float *dB, float *dC, size_t n,
 /* ---- a1: the launch loop, in-process -----------------------------------------------
  * Replaces the 5000-process bash loop (cuda-test-deployment.yaml:19): `iters`
  * back-to-back launches on `stream`; graph_batch > 1 captures that many launches into
- * one CUDA graph and replays it (launch-bound sizes).  Asynchronous. */
+ * one CUDA graph and replays it (launch-bound sizes).  Asynchronous, except that the
+ * graph form (graph_batch > 1) drains the stream before returning; any capturable or
+ * legacy stream is accepted (the capture happens on a private stream). */
 int b200va_add_f32_loop(const float *dA, const float *dB, float *dC, size_t n,
                         int variant, int iters, int graph_batch, void *stream);
+/* Persistent form for a long-running load generator: the graph of `graph_batch` launches
+ * is captured once; b200va_loop_run replays it floor(iters/graph_batch) times plus
+ * iters%graph_batch direct launches, asynchronously on `stream`.  Destroy only after
+ * the stream has drained. */
+typedef struct b200va_loop b200va_loop_t;
+int b200va_loop_create(b200va_loop_t **out, const float *dA, const float *dB, float *dC,
+                       size_t n, int variant, int graph_batch);
+int b200va_loop_run(b200va_loop_t *loop, int iters, void *stream);
+int b200va_loop_destroy(b200va_loop_t *loop);
 
 /* ---- a2: input recipes ---------------------------------------------------------------
  * Host: the sample's recipe  h_A[i] = rand()/(float)RAND_MAX; h_B[i] = ... interleaved,

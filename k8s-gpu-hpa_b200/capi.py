@@ -62,6 +62,9 @@ _SIGS = {
     "b200va_add_f32": (_I, [_P, _P, _P, _SZ, _I, _P]),
     "b200va_add_f32_tuned": (_I, [_P, _P, _P, _SZ, C.POINTER(Tune), _P]),
     "b200va_add_f32_loop": (_I, [_P, _P, _P, _SZ, _I, _I, _I, _P]),
+    "b200va_loop_create": (_I, [C.POINTER(_P), _P, _P, _P, _SZ, _I, _I]),
+    "b200va_loop_run": (_I, [_P, _I, _P]),
+    "b200va_loop_destroy": (_I, [_P]),
     "b200va_host_fill_rand_f32": (_I, [_P, _P, _SZ]),
     "b200va_host_fill_ctr_f32": (_I, [_P, _SZ, _U64, _U64]),
     "b200va_fill_ctr_f32": (_I, [_P, _SZ, _U64, _U64, _P]),

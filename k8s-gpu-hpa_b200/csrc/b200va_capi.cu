@@ -9,7 +9,12 @@
 // point returns an error code.
 #include <cuda_runtime.h>
 
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <atomic>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -227,6 +232,36 @@ int check_args(const float* dA, const float* dB, const float* dC, size_t n)
     return B200VA_OK;
 }
 
+// All hot-path launches go through here: programmatic stream serialization lets launch
+// k+1 ramp up behind launch k's tail (the kernels call griddepcontrol.wait before their
+// first global access, so stream order is unchanged).  B200VA_NO_PDL=1 disables it.
+thread_local bool tl_pdl_off = false;   // set while re-capturing a graph without PDL edges
+
+bool pdl_enabled()
+{
+    static const bool on = [] {
+        const char* e = std::getenv("B200VA_NO_PDL");
+        return !(e && e[0] == '1');
+    }();
+    return on && !tl_pdl_off;
+}
+
+template <class... KArgs, class... Args>
+int launch_kernel(void (*fn)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cuda_err(cudaLaunchKernelEx(&cfg, fn, static_cast<KArgs>(args)...));
+}
+
 int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t t, cudaStream_t stream)
 {
     RC_TRY(check_args(dA, dB, dC, n));
@@ -259,8 +294,7 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
     if (vw == 0) {  // scalar control / mixed misalignment
         const size_t blocks = (n + 255) / 256;
         if (blocks > 0x7fffffffull) return B200VA_ERR_INVALID;
-        vadd_scalar<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(dA, dB, dC, n);
-        return cuda_err(cudaGetLastError());
+        return launch_kernel(vadd_scalar, static_cast<unsigned>(blocks), 256u, 0, stream, dA, dB, dC, n);
     }
     if (head > n) head = n;
     const size_t nvec = (n - head) / static_cast<size_t>(vw);
@@ -280,9 +314,9 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
         size_t grid = static_cast<size_t>(di->sm_count) * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1);
         if (grid > ntiles) grid = ntiles;
         if (grid == 0) grid = 1;
-        fn<<<static_cast<unsigned>(grid), t.threads + 32, static_cast<size_t>(smem), stream>>>(
-            dA, dB, dC, n, head, nvec, static_cast<uint32_t>(t.tile_bytes), static_cast<uint32_t>(t.stages));
-        return cuda_err(cudaGetLastError());
+        return launch_kernel(fn, static_cast<unsigned>(grid), static_cast<unsigned>(t.threads + 32),
+                             static_cast<size_t>(smem), stream, dA, dB, dC, n, head, nvec,
+                             static_cast<uint32_t>(t.tile_bytes), static_cast<uint32_t>(t.stages));
     }
 
     if (t.threads < 32 || t.threads > 1024 || (t.threads & 31)) return B200VA_ERR_VARIANT;
@@ -300,8 +334,8 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
     }
     if (grid > 0x7fffffffull) grid = 0x7fffffffull;   // kernel loops tile += gridDim.x
     if (grid == 0) grid = 1;
-    fn<<<static_cast<unsigned>(grid), t.threads, 0, stream>>>(dA, dB, dC, n, head, nvec, ntiles);
-    return cuda_err(cudaGetLastError());
+    return launch_kernel(fn, static_cast<unsigned>(grid), static_cast<unsigned>(t.threads), 0, stream, dA, dB, dC,
+                         n, head, nvec, ntiles);
 }
 
 unsigned support_grid(const b200va_devinfo_t* di, size_t n, int threads)
@@ -410,40 +444,112 @@ int b200va_add_f32_tuned(const float* dA, const float* dB, float* dC, size_t n,
     return launch(dA, dB, dC, n, t, static_cast<cudaStream_t>(stream));
 }
 
-int b200va_add_f32_loop(const float* dA, const float* dB, float* dC, size_t n, int variant,
-                        int iters, int graph_batch, void* stream)
+// ---- a1: the launch loop --------------------------------------------------------------
+struct b200va_loop {
+    const float *dA = nullptr, *dB = nullptr;
+    float* dC = nullptr;
+    size_t n = 0;
+    b200va_tune_t tune{};
+    int batch = 1;
+    int device = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool pdl_edges = false;
+};
+
+static int capture_batch(b200va_loop* l, cudaStream_t cap)
+{
+    CU_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    int rc = B200VA_OK;
+    for (int i = 0; i < l->batch && rc == B200VA_OK; ++i) rc = launch(l->dA, l->dB, l->dC, l->n, l->tune, cap);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(cap, &g);
+    if (rc != B200VA_OK || e != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return rc != B200VA_OK ? rc : cuda_err(e);
+    }
+    cudaGraphExec_t x = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&x, g, 0);
+    if (e2 != cudaSuccess) { cudaGraphDestroy(g); cudaGetLastError(); return cuda_err(e2); }
+    l->graph = g;
+    l->exec = x;
+    return B200VA_OK;
+}
+
+int b200va_loop_destroy(b200va_loop_t* l)
+{
+    if (!l) return B200VA_OK;
+    if (l->exec) cudaGraphExecDestroy(l->exec);
+    if (l->graph) cudaGraphDestroy(l->graph);
+    delete l;
+    return B200VA_OK;
+}
+
+int b200va_loop_create(b200va_loop_t** out, const float* dA, const float* dB, float* dC, size_t n, int variant,
+                       int graph_batch)
+{
+    if (!out || graph_batch < 0) return B200VA_ERR_INVALID;
+    *out = nullptr;
+    if (variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
+    RC_TRY(check_args(dA, dB, dC, n));
+    b200va_loop* l = new (std::nothrow) b200va_loop;
+    if (!l) return B200VA_ERR_NOMEM;
+    l->dA = dA; l->dB = dB; l->dC = dC; l->n = n;
+    l->batch = graph_batch > 1 ? graph_batch : 1;
+    default_tune(variant, n, &l->tune);
+    cudaError_t e = cudaGetDevice(&l->device);
+    if (e != cudaSuccess) { delete l; return cuda_err(e); }
+    if (l->batch > 1 && n > 0) {
+        cudaStream_t cap = nullptr;
+        e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete l; return cuda_err(e); }
+        int rc = capture_batch(l, cap);
+        l->pdl_edges = (rc == B200VA_OK) && pdl_enabled();
+        if (rc != B200VA_OK && pdl_enabled()) {   // older drivers: capture without programmatic edges
+            tl_pdl_off = true;
+            rc = capture_batch(l, cap);
+            tl_pdl_off = false;
+        }
+        cudaStreamDestroy(cap);
+        if (rc != B200VA_OK) { delete l; return rc; }
+    }
+    *out = l;
+    return B200VA_OK;
+}
+
+int b200va_loop_run(b200va_loop_t* l, int iters, void* stream)
+{
+    if (!l || iters < 0) return B200VA_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int left = iters;
+    if (l->exec) {
+        for (; left >= l->batch; left -= l->batch) CU_TRY(cudaGraphLaunch(l->exec, st));
+    }
+    for (; left > 0; --left) RC_TRY(launch(l->dA, l->dB, l->dC, l->n, l->tune, st));
+    return B200VA_OK;
+}
+
+int b200va_add_f32_loop(const float* dA, const float* dB, float* dC, size_t n, int variant, int iters,
+                        int graph_batch, void* stream)
 {
     if (iters < 0 || graph_batch < 0) return B200VA_ERR_INVALID;
     if (variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    b200va_tune_t t;
-    default_tune(variant, n, &t);
     if (graph_batch <= 1 || iters < graph_batch) {
+        b200va_tune_t t;
+        default_tune(variant, n, &t);
         for (int i = 0; i < iters; ++i) RC_TRY(launch(dA, dB, dC, n, t, st));
         return B200VA_OK;
     }
-    if (st == nullptr || st == cudaStreamLegacy) return B200VA_ERR_INVALID;  // not capturable
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    CU_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = B200VA_OK;
-    for (int i = 0; i < graph_batch && rc == B200VA_OK; ++i) rc = launch(dA, dB, dC, n, t, st);
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
-    if (rc != B200VA_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-    CU_TRY(e);
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    if (e != cudaSuccess) { cudaGraphDestroy(graph); return cuda_err(e); }
-    const int reps = iters / graph_batch, rest = iters % graph_batch;
-    for (int r = 0; r < reps && e == cudaSuccess; ++r) e = cudaGraphLaunch(exec, st);
-    for (int i = 0; i < rest && e == cudaSuccess && rc == B200VA_OK; ++i) rc = launch(dA, dB, dC, n, t, st);
-    // the executable graph must outlive its launches: graph mode drains the stream
-    cudaError_t e2 = cudaStreamSynchronize(st);
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
-    if (rc != B200VA_OK) return rc;
-    CU_TRY(e);
-    CU_TRY(e2);
-    return B200VA_OK;
+    b200va_loop_t* l = nullptr;
+    RC_TRY(b200va_loop_create(&l, dA, dB, dC, n, variant, graph_batch));
+    int rc = b200va_loop_run(l, iters, stream);
+    // the executable graph must outlive its launches: the one-shot form drains the stream
+    const cudaError_t e = cudaStreamSynchronize(st);
+    b200va_loop_destroy(l);
+    if (rc == B200VA_OK) rc = cuda_err(e);
+    return rc;
 }
 
 // ------------------------------------------------------------------ a2: input recipes
@@ -557,10 +663,68 @@ struct b200va_stager {
     float last_ms = 0.f;
 };
 
+// NUMA node the current CUDA device hangs off (sysfs), or -1.  B200VA_NUMA_NODE overrides.
+static int device_numa_node()
+{
+    if (const char* e = std::getenv("B200VA_NUMA_NODE")) return std::atoi(e);
+    int dev = 0;
+    char bus[32] = {0}, path[128];
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) return -1;
+    for (char* c = bus; *c; ++c) *c = static_cast<char>(std::tolower(*c));
+    std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (FILE* f = std::fopen(path, "r")) {
+        if (std::fscanf(f, "%d", &node) != 1) node = -1;
+        std::fclose(f);
+    }
+    return node;
+}
+
+// Parses a sysfs cpulist ("0-31,64-95") into a cpu_set_t restricted to `allowed`.
+static bool node_cpuset(int node, const cpu_set_t& allowed, cpu_set_t* out)
+{
+    char path[96], buf[4096];
+    std::snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = std::fopen(path, "r");
+    if (!f) return false;
+    const bool ok = std::fgets(buf, sizeof buf, f) != nullptr;
+    std::fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(out);
+    int count = 0;
+    for (char* p = buf; *p && *p != '\n';) {
+        char* end = nullptr;
+        long lo = std::strtol(p, &end, 10), hi = lo;
+        if (end == p) break;
+        if (*end == '-') hi = std::strtol(end + 1, &end, 10);
+        for (long c = lo; c <= hi && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &allowed)) { CPU_SET(c, out); ++count; }
+        p = (*end == ',') ? end + 1 : end;
+    }
+    return count > 0;
+}
+
+// Pinned, mapped host memory whose pages sit on the NUMA node local to the current GPU:
+// the calling thread is moved onto that node's CPUs (and its memory policy set to prefer
+// the node) for the duration of the allocation, so the first touch inside cudaHostAlloc
+// lands there; a PCIe DMA then never crosses the inter-socket link.
 int b200va_host_alloc(void** out, size_t bytes)
 {
     if (!out) return B200VA_ERR_INVALID;
-    CU_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+    const int node = device_numa_node();
+    cpu_set_t old_set, node_set;
+    bool moved = false, policy = false;
+    if (node >= 0 && sched_getaffinity(0, sizeof old_set, &old_set) == 0 && node_cpuset(node, old_set, &node_set)) {
+        moved = sched_setaffinity(0, sizeof node_set, &node_set) == 0;
+        if (node < 64) {
+            unsigned long mask = 1ul << node;
+            policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0;
+        }
+    }
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+    CU_TRY(e);
     return B200VA_OK;
 }
 

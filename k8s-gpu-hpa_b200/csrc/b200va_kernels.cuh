@@ -33,6 +33,8 @@ namespace b200va {
 __global__ void vadd_scalar(const float* A, const float* B, float* C, size_t n)
 {
     const size_t i = static_cast<size_t>(blockDim.x) * blockIdx.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (i < n) C[i] = __fadd_rn(A[i], B[i]);
 }
 
@@ -91,6 +93,8 @@ __global__ void vadd_vec(const float* A, const float* B, float* C, size_t n, siz
     const float* b = B + head;
     float* c = C + head;
     const size_t tile_vecs = static_cast<size_t>(blockDim.x) * UNROLL;
+    pdl_launch_dependents();
+    pdl_wait();   // everything above overlapped the previous launch's tail
 
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t v0 = tile * tile_vecs + threadIdx.x;
@@ -164,6 +168,8 @@ vadd_tma(const float* A, const float* B, float* C, size_t n, size_t head, size_t
 
     uint64_t pol = 0;
     if constexpr (L2_HINT || ST == ST_NA_EF) pol = l2_evict_first_policy();
+    pdl_launch_dependents();
+    pdl_wait();   // barrier init and address math overlapped the previous launch's tail
 
     if (threadIdx.x < 32) {
         // ------------------------------------------------------------ producer

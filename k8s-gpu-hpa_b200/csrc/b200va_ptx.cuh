@@ -244,6 +244,22 @@ __device__ __forceinline__ void fence_proxy_async_smem()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// Programmatic dependent launch (sm_90+).  `pdl_launch_dependents` lets the NEXT kernel in
+// the stream start scheduling its CTAs as soon as every CTA of this grid has issued it
+// (or exited); `pdl_wait` blocks until the PREVIOUS grid has completed and its memory
+// operations are visible.  Together they hide launch latency and CTA ramp-up behind the
+// previous launch's tail without weakening stream order.  Both are no-ops for a launch
+// without the programmatic-stream-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+__device__ __forceinline__ void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // Named barrier over a subset of the CTA's warps (id 1..15; 0 is __syncthreads).
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
 {

@@ -373,6 +373,7 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     b200va_stager_t* stager = nullptr;
+    b200va_loop_t* loop = nullptr;
     const bool staged = o.mode == "staged";
     if (ok) {
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "create stream");
@@ -394,7 +395,8 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
             VA(b200va_fill_ctr_f32(dA, m, 0x0A, b, st), "generate A");   // global index => sharding invisible
             VA(b200va_fill_ctr_f32(dB, m, 0x0B, b, st), "generate B");
             // warm-up
-            VA(b200va_add_f32_loop(dA, dB, dC, m, o.variant, 3, 0, st), "warm up");
+            VA(b200va_loop_create(&loop, dA, dB, dC, m, o.variant, o.graph), "capture launch loop");
+            VA(b200va_loop_run(loop, std::max(3, o.graph), st), "warm up");
             CK(cudaStreamSynchronize(st), "warm up");
         }
     }
@@ -408,7 +410,7 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
             }
         } else {
             CK(cudaEventRecord(e0, st), "record event");
-            VA(b200va_add_f32_loop(dA, dB, dC, m, o.variant, o.iters, o.graph, st), "launch vectorAdd kernel");
+            VA(b200va_loop_run(loop, o.iters, st), "launch vectorAdd kernel");
             CK(cudaEventRecord(e1, st), "record event");
             CK(cudaEventSynchronize(e1), "synchronize");
             float ms = 0; if (ok) CK(cudaEventElapsedTime(&ms, e0, e1), "read event");
@@ -463,6 +465,8 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
             r.mismatches = h[0]; r.first_bad = h[0] ? b + h[1] : ~0ull; r.digest[0] = h[2]; r.digest[1] = h[3];
         }
     }
+    if (st) cudaStreamSynchronize(st);
+    if (loop) b200va_loop_destroy(loop);
     if (stager) b200va_stager_destroy(stager);
     b200va_host_free(hA); b200va_host_free(hB); b200va_host_free(hC);
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dRes);

@@ -140,6 +140,29 @@ def _host_ptr(x, name: str) -> int:
     raise TypeError(f"{name} must be a float32 numpy array or CPU tensor")
 
 
+class PinnedBuffer:
+    """Pinned, GPU-local-NUMA host memory from b200va_host_alloc, viewed as a float32 numpy
+    array (``.array``).  The memory lives until ``free()`` / garbage collection."""
+
+    def __init__(self, n: int):
+        self._p = C.c_void_p()
+        self.n = n
+        check(lib.b200va_host_alloc(C.byref(self._p), max(1, n) * 4), "b200va_host_alloc")
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_float)), shape=(n,))
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib.b200va_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Stager:
     """Host-buffer path (a3 + a4 + a6-copy): H2D, add and D2H pipelined in chunks."""
 

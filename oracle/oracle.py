@@ -34,6 +34,7 @@ for _n, _r, _a in [
     ("oracle_bits_digest_u32", None, [_P, _SZ, _P]),
     ("oracle_vadd_digest_f32", None, [_P, _P, _SZ, _P]),
     ("oracle_num_cpus", _I, []),
+    ("oracle_cpu_quota", C.c_double, []),
     ("oracle_vadd_f32_mt", None, [_P, _P, _P, _SZ, _I]),
     ("oracle_fill_ctr_pair_mt", None, [_P, _P, _P, _SZ, _U64, _U64, _U64, _I]),
     ("oracle_vadd_digest_f32_mt", None, [_P, _P, _SZ, _I, _P]),
@@ -137,6 +138,25 @@ def ctr_vadd_digest(n: int, first: int = 0, threads: int = 0, block: int = 1 << 
 
 def num_cpus() -> int:
     return int(_lib.oracle_num_cpus())
+
+
+def cpu_quota() -> float:
+    """Container CPU quota in CPUs (0 = unlimited)."""
+    return float(_lib.oracle_cpu_quota())
+
+
+def best_thread_count(n: int = 1 << 26) -> tuple[int, dict[int, float]]:
+    """All the host threads the add can USE: tries the affinity count, the cgroup quota and
+    a few in between on a short sample and returns the fastest (threads, {threads: elem/s})."""
+    ncpu, quota = num_cpus(), cpu_quota()
+    cands = {ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 8), min(ncpu, 16), min(ncpu, 32)}
+    if quota > 0:
+        cands |= {max(1, min(ncpu, int(round(quota)))), max(1, min(ncpu, int(round(2 * quota))))}
+    rates = {}
+    for t in sorted(cands):
+        secs = time_vadd_mt(n, t, 1, 2)
+        rates[t] = n / min(secs)
+    return max(rates, key=rates.get), rates
 
 
 def time_vadd_mt(n: int, threads: int = 0, warmup: int = 1, reps: int = 5) -> list[float]:

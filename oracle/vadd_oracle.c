@@ -32,6 +32,7 @@
 #include <sched.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -226,6 +227,24 @@ int oracle_num_cpus(void)
     }
     long c = sysconf(_SC_NPROCESSORS_ONLN);
     return c > 0 ? (int)c : 1;
+}
+
+/* CPU bandwidth quota of the container in whole CPUs (cgroup v2 cpu.max or v1 cfs quota),
+ * 0 if unlimited/unknown.  More runnable threads than this only get throttled. */
+double oracle_cpu_quota(void)
+{
+    FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (f) {
+        char q[64]; double period = 0;
+        int n = fscanf(f, "%63s %lf", q, &period);
+        fclose(f);
+        if (n == 2 && strcmp(q, "max") != 0 && period > 0) return atof(q) / period;
+        return 0.0;
+    }
+    double quota = -1, period = 0;
+    if ((f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r"))) { if (fscanf(f, "%lf", &quota) != 1) quota = -1; fclose(f); }
+    if ((f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r"))) { if (fscanf(f, "%lf", &period) != 1) period = 0; fclose(f); }
+    return (quota > 0 && period > 0) ? quota / period : 0.0;
 }
 
 typedef struct {

@@ -258,7 +258,19 @@ def test_launch_loop_matches_single_launch_with_and_without_graphs():
             va.add_loop(a, b, c, iters, graph_batch=batch)
             s.synchronize()
             assert va.digest(c) == want, (iters, batch)
-    # the legacy default stream cannot be captured: graph mode refuses it
+    # the legacy default stream is fine too: the batch is captured on a private stream
     c = torch.zeros_like(a)
     rc = capi.lib.b200va_add_f32_loop(a.data_ptr(), b.data_ptr(), c.data_ptr(), n, 0, 20, 10, None)
-    assert rc == capi.ERR_INVALID
+    assert rc == capi.OK
+    torch.cuda.synchronize()
+    assert va.digest(c) == want
+    # persistent loop handle: one capture, many replays
+    import ctypes as C
+    h = C.c_void_p()
+    c = torch.zeros_like(a)
+    assert capi.lib.b200va_loop_create(C.byref(h), a.data_ptr(), b.data_ptr(), c.data_ptr(), n, 0, 16) == capi.OK
+    for iters in (16, 40, 3):
+        assert capi.lib.b200va_loop_run(h, iters, s.cuda_stream) == capi.OK
+    s.synchronize()
+    assert capi.lib.b200va_loop_destroy(h) == capi.OK
+    assert va.digest(c) == want

@@ -14,6 +14,8 @@ if has info; then
   nvidia-smi > "$OUT/nvidia-smi.txt" 2>&1
   nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit,memory.total --format=csv >> "$OUT/nvidia-smi.txt" 2>&1
   nproc > "$OUT/host.txt"; lscpu | head -25 >> "$OUT/host.txt"; free -g >> "$OUT/host.txt"
+  { echo "cgroup cpu.max: $(cat /sys/fs/cgroup/cpu.max 2>&1)"; echo "cfs quota: $(cat /sys/fs/cgroup/cpu/cpu.cfs_quota_us 2>&1) / $(cat /sys/fs/cgroup/cpu/cpu.cfs_period_us 2>&1)";
+    lscpu | grep -i numa; nvidia-smi topo -m; for d in /sys/bus/pci/devices/*; do [ "$(cat $d/vendor 2>/dev/null)" = "0x10de" ] && echo "$d numa_node=$(cat $d/numa_node)"; done; } >> "$OUT/host.txt" 2>&1
 fi
 
 if has smoke; then
@@ -26,6 +28,40 @@ if has sweep; then
   echo "sweep 2^28 exit=$?" | tee -a "$OUT/status.txt"
   timeout 600 $PKG/b200va_tune --n $((1<<24)) --reps 50 --warmup 5 < "$OUT/geometries.txt" > "$OUT/tune_2p24.jsonl" 2> "$OUT/tune_2p24.err"
   echo "sweep 2^24 exit=$?" | tee -a "$OUT/status.txt"
+fi
+
+if has ab; then
+  python tools/gen_ab.py > "$OUT/ab_geometries.txt"
+  for lg in 28 24 22 20; do
+    reps=20; [ $lg -le 24 ] && reps=200; [ $lg -le 20 ] && reps=1000
+    timeout 900 $PKG/b200va_tune --n $((1<<lg)) --reps $reps --warmup 3 --rounds 7 < "$OUT/ab_geometries.txt" > "$OUT/ab_2p$lg.jsonl" 2> "$OUT/ab_2p$lg.err"
+    echo "ab 2^$lg exit=$?" | tee -a "$OUT/status.txt"
+  done
+  for lg in 28 24; do
+    reps=20; [ $lg -le 24 ] && reps=200
+    B200VA_NO_PDL=1 timeout 900 $PKG/b200va_tune --n $((1<<lg)) --reps $reps --warmup 3 --rounds 7 < "$OUT/ab_geometries.txt" > "$OUT/ab_nopdl_2p$lg.jsonl" 2>> "$OUT/ab_2p$lg.err"
+  done
+fi
+
+if has nsweep; then
+  timeout 900 $PKG/b200va_sweep --lo 16 --hi 30 > "$OUT/sweep_n.jsonl" 2> "$OUT/sweep_n.err"; echo "nsweep exit=$?" | tee -a "$OUT/status.txt"
+fi
+
+if has e2e; then
+  timeout 900 python tools/e2e_sweep.py > "$OUT/e2e_sweep.jsonl" 2> "$OUT/e2e_sweep.err"; echo "e2e sweep exit=$?" | tee -a "$OUT/status.txt"
+fi
+
+if has sanitizer; then
+  for k in auto k0 k1 k2 k3; do
+    timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 $PKG/vectorAdd --n 300007 --iters 2 --kernel $k > "$OUT/sanitizer_memcheck_$k.log" 2>&1
+    echo "memcheck $k exit=$?" | tee -a "$OUT/status.txt"
+  done
+  timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 $PKG/vectorAdd --n 300007 --iters 2 --kernel k2 > "$OUT/sanitizer_racecheck_k2.log" 2>&1
+  echo "racecheck k2 exit=$?" | tee -a "$OUT/status.txt"
+  timeout 600 compute-sanitizer --tool initcheck --error-exitcode 9 $PKG/vectorAdd --n 300007 --iters 2 --kernel k2 > "$OUT/sanitizer_initcheck_k2.log" 2>&1
+  echo "initcheck k2 exit=$?" | tee -a "$OUT/status.txt"
+  timeout 600 compute-sanitizer --tool synccheck --error-exitcode 9 $PKG/vectorAdd --n 300007 --iters 2 --kernel k2 > "$OUT/sanitizer_synccheck_k2.log" 2>&1
+  echo "synccheck k2 exit=$?" | tee -a "$OUT/status.txt"
 fi
 
 if has tests; then

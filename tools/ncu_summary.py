@@ -14,8 +14,11 @@ KEEP = {
     "gpu__time_duration.sum": "duration_ns",
     "dram__bytes_read.sum": "dram_read_bytes",
     "dram__bytes_write.sum": "dram_write_bytes",
-    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak",
-    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "gpu_dram_pct_of_peak",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak",
+    "dram__cycles_active.max.pct_of_peak_sustained_elapsed": "dram_busiest_channel_pct",
+    "dram__cycles_active.min.pct_of_peak_sustained_elapsed": "dram_idlest_channel_pct",
+    "dram__bytes.sum.peak_sustained": "dram_peak_bytes_per_cycle",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
     "dram__cycles_active.avg.pct_of_peak_sustained_elapsed": "dram_cycles_active_pct",
     "lts__t_sector_hit_rate.pct": "l2_hit_rate_pct",
     "lts__t_bytes.sum": "l2_bytes",
@@ -51,8 +54,9 @@ def read_raw(rep: str):
                     v = float(val.replace(",", ""))
                 except ValueError:
                     continue
-                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "usecond": 1e3, "msecond": 1e6, "nsecond": 1,
-                         "second": 1e9, "Ghz": 1e9, "Mhz": 1e6, "hz": 1}.get(unit, 1)
+                scale = {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "us": 1e3, "ms": 1e6, "ns": 1,
+                         "usecond": 1e3, "msecond": 1e6, "nsecond": 1, "s": 1e9, "second": 1e9, "Ghz": 1e9, "Mhz": 1e6,
+                         "hz": 1}.get(unit, 1)
                 if KEEP[col].endswith(("_bytes", "_ns", "_hz")):
                     v *= scale
                 d[KEEP[col]] = v
@@ -60,6 +64,10 @@ def read_raw(rep: str):
             d["dram_bytes"] = d["dram_read_bytes"] + d["dram_write_bytes"]
             if d.get("duration_ns"):
                 d["dram_GBps"] = d["dram_bytes"] / d["duration_ns"]
+            if d.get("dram_peak_bytes_per_cycle") and d.get("dram_clock_hz"):
+                # ncu reports Kbyte/cycle for the chip-wide sum (2.048 -> 2048 B/cycle)
+                bpc = d["dram_peak_bytes_per_cycle"] * (1e3 if d["dram_peak_bytes_per_cycle"] < 100 else 1)
+                d["dram_pin_peak_GBps"] = bpc * d["dram_clock_hz"] / 1e9
         res.append(d)
     return res
 
@@ -83,7 +91,7 @@ def main():
     json.dump(allk, open(args.out + "_ncu.json", "w"), indent=1)
     cols = ["report", "kernel", "grid", "block", "registers_per_thread", "dyn_smem_bytes", "duration_ns", "algorithmic_GBps",
             "dram_GBps", "dram_bytes", "traffic_over_algorithmic", "dram_pct_of_peak", "l2_hit_rate_pct",
-            "achieved_occupancy_pct", "sm_clock_hz"]
+            "dram_busiest_channel_pct", "dram_idlest_channel_pct", "achieved_occupancy_pct", "sm_clock_hz", "dram_clock_hz"]
     with open(args.out + "_ncu.md", "w") as f:
         f.write("| " + " | ".join(cols) + " |\n|" + "---|" * len(cols) + "\n")
         for d in allk:
