@@ -65,7 +65,7 @@ typedef struct b200va_tune {
     int threads;      /* CTA size (vec kernels) or consumer threads (TMA kernel)        */
     int unroll;       /* vec: vectors per thread per tile: 1,2,4,8                      */
     int ctas_per_sm;  /* 0: one tile per CTA; >0: persistent grid = SMs * ctas_per_sm   */
-    int ld_hint;      /* 0 plain, 1 L1::no_allocate, 2 .cs, 3 no_allocate+L2 evict_first, 4 .nc+no_allocate */
+    int ld_hint;      /* 0 plain, 1 L1::no_allocate, 2 .cs, 3 no_allocate+L2 evict_first, 4 .nc+no_allocate, 5 no_allocate+L2::256B */
     int st_hint;      /* 0 plain, 1 L1::no_allocate,   2 .cs, 3 no_allocate+L2 evict_first */
     int stages;       /* TMA: ring depth (2..16)                                        */
     int tile_bytes;   /* TMA: bytes per array per stage (multiple of 2048)              */

@@ -104,6 +104,7 @@ vec_fn pick_ld(int ld, int st)
         case LD_NC_NA: return pick_st<VW, UNROLL, LD_NC_NA>(st);
         case LD_CS:    return pick_st<VW, UNROLL, LD_CS>(st);
         case LD_NA_EF: return pick_st<VW, UNROLL, LD_NA_EF>(st);
+        case LD_NA_256: return pick_st<VW, UNROLL, LD_NA_256>(st);
     }
     return nullptr;
 }
@@ -171,7 +172,12 @@ int ensure_smem_optin(tma_fn fn, int device, int bytes)
 }
 
 // ----------------------------------------------------------------------- geometry
-// Production choices per size class.  Tuned on B200 (profiles/): see DESIGN.md.
+// Production choices per size class, from the interleaved A/B sweeps on B200
+// (profiles/r01/b_ab_2p{20,22,24,28}.jsonl; median of 7 rounds of back-to-back launches):
+//   n >= 2^26  HBM streaming           K1 128-bit, 512 threads, 1 vector/thread, stores skip L1   7.25 TB/s @2^28
+//   2^23 < n   footprint a few x L2    K3 256-bit, 128 threads, L2 evict-first loads, plain stores 7.36 TB/s @2^24
+//   n <= 2^23  L2-resident             K1 128-bit, 256 threads x2, plain hints (let L2 keep it)    11.7 TB/s @2^22
+//   n <  2^21  launch-bound            K1 128-bit, 512 (>=2^19) / 128 threads x1
 void default_tune(int variant, size_t n, b200va_tune_t* t)
 {
     std::memset(t, 0, sizeof *t);
@@ -183,36 +189,43 @@ void default_tune(int variant, size_t n, b200va_tune_t* t)
             return;
         case B200VA_K2_TMA:
             t->kind = B200VA_K2_TMA;
-            t->threads = 256;          // consumer threads (+32 producer)
+            t->threads = 128;          // consumer threads (+32 producer)
             t->ctas_per_sm = 1;
             t->ld_hint = LD_PLAIN;
             t->st_hint = ST_NA;
-            t->stages = 6;
-            t->tile_bytes = 16384;
-            t->store_mode = 1;
+            t->stages = 4;
+            t->tile_bytes = 8192;
+            t->store_mode = 0;
             return;
         case B200VA_K1_VEC128:
             t->kind = B200VA_K1_VEC128;
-            break;
+            t->threads = n < (size_t{1} << 19) ? 128 : 512;
+            t->unroll = 1;
+            t->ld_hint = LD_PLAIN;
+            t->st_hint = ST_NA;
+            return;
         case B200VA_K3_VEC256:
-        case B200VA_K_AUTO:
-        default:
             t->kind = B200VA_K3_VEC256;
+            t->threads = n < (size_t{1} << 26) ? 128 : 1024;
+            t->unroll = 1;
+            t->ld_hint = n < (size_t{1} << 26) ? LD_NA_EF : LD_PLAIN;
+            t->st_hint = n < (size_t{1} << 26) ? ST_PLAIN : ST_NA;
+            return;
+        default:
             break;
     }
-    t->ld_hint = LD_NA;
-    t->st_hint = ST_NA;
-    t->ctas_per_sm = 0;
-    if (n < (size_t{1} << 20)) {        // launch-bound: spread over as many SMs as possible
-        t->kind = B200VA_K1_VEC128;
-        t->threads = 128;
-        t->unroll = 1;
-    } else if (n < (size_t{1} << 24)) {
-        t->threads = 256;
-        t->unroll = 2;
+    // B200VA_K_AUTO
+    t->unroll = 1;
+    if (n >= (size_t{1} << 26)) {
+        t->kind = B200VA_K1_VEC128; t->threads = 512; t->ld_hint = LD_PLAIN; t->st_hint = ST_NA;
+    } else if (n > (size_t{1} << 23)) {
+        t->kind = B200VA_K3_VEC256; t->threads = 128; t->ld_hint = LD_NA_EF; t->st_hint = ST_PLAIN;
+    } else if (n >= (size_t{1} << 21)) {
+        t->kind = B200VA_K1_VEC128; t->threads = 256; t->unroll = 2; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
+    } else if (n >= (size_t{1} << 19)) {
+        t->kind = B200VA_K1_VEC128; t->threads = 512; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
     } else {
-        t->threads = 512;
-        t->unroll = (t->kind == B200VA_K3_VEC256) ? 2 : 4;
+        t->kind = B200VA_K1_VEC128; t->threads = 128; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
     }
 }
 
@@ -294,7 +307,9 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
     if (vw == 0) {  // scalar control / mixed misalignment
         const size_t blocks = (n + 255) / 256;
         if (blocks > 0x7fffffffull) return B200VA_ERR_INVALID;
-        return launch_kernel(vadd_scalar, static_cast<unsigned>(blocks), 256u, 0, stream, dA, dB, dC, n);
+        // the control keeps the sample's plain launch (no programmatic dependent launch)
+        vadd_scalar<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(dA, dB, dC, n);
+        return cuda_err(cudaGetLastError());
     }
     if (head > n) head = n;
     const size_t nvec = (n - head) / static_cast<size_t>(vw);
@@ -762,7 +777,7 @@ int b200va_stager_create(b200va_stager_t** out, int device, size_t chunk_elems, 
 {
     if (!out) return B200VA_ERR_INVALID;
     *out = nullptr;
-    if (chunk_elems == 0) chunk_elems = size_t{1} << 22;   // 16 MiB per array per slot
+    if (chunk_elems == 0) chunk_elems = size_t{1} << 23;   // 32 MiB per array per slot (e2e sweep: 8-16 Mi best)
     if (depth == 0) depth = 3;
     if (depth < 1 || depth > 16) return B200VA_ERR_INVALID;
     chunk_elems = (chunk_elems + 63) & ~size_t{63};        // slots stay 256-B aligned
@@ -851,7 +866,7 @@ int b200va_stager_last_ms(b200va_stager_t* s, float* ms)
 int b200va_add_f32_host(const float* hA, const float* hB, float* hC, size_t n, int device, int variant)
 {
     b200va_stager_t* s = nullptr;
-    size_t chunk = size_t{1} << 22;
+    size_t chunk = size_t{1} << 23;
     if (n < chunk) chunk = n ? n : 1;
     RC_TRY(b200va_stager_create(&s, device, chunk, n > chunk ? 3 : 1));
     const int rc = b200va_stager_add_f32(s, hA, hB, hC, n, variant, 0);

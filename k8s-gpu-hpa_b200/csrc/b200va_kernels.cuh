@@ -33,8 +33,6 @@ namespace b200va {
 __global__ void vadd_scalar(const float* A, const float* B, float* C, size_t n)
 {
     const size_t i = static_cast<size_t>(blockDim.x) * blockIdx.x + threadIdx.x;
-    pdl_launch_dependents();
-    pdl_wait();
     if (i < n) C[i] = __fadd_rn(A[i], B[i]);
 }
 

@@ -17,7 +17,8 @@ enum : int {
     LD_NA_EF = 3,   // L1::no_allocate + L2 evict_first         (policy operand / .L2::evict_first on 256-bit)
     LD_NC_NA = 4,   // ld.global.nc.L1::no_allocate             (read-only path; NOTE ptxas is then free to
                     //   sink the loads next to their use, which serialises the batch -- kept as a control)
-    LD_HINTS = 5
+    LD_NA_256 = 5,  // L1::no_allocate + L2::256B prefetch size (SASS LTC256B): L2 fetches 256-B granules
+    LD_HINTS = 6
 };
 // Store hints (tune.st_hint)
 enum : int {
@@ -54,6 +55,9 @@ __device__ __forceinline__ f32x4 ldg128(const float* p, uint64_t pol)
                      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
     else if constexpr (HINT == LD_CS)
         asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    else if constexpr (HINT == LD_NA_256)
+        asm volatile("ld.global.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
                      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
     else
         asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
@@ -100,6 +104,10 @@ __device__ __forceinline__ f32x8 ldg256(const float* p, uint64_t pol)
                        "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p) : "memory");
     else if constexpr (HINT == LD_CS)
         asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]),
+                       "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p) : "memory");
+    else if constexpr (HINT == LD_NA_256)
+        asm volatile("ld.global.L1::no_allocate.L2::256B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]),
                        "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p) : "memory");
     else

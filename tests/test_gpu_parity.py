@@ -160,7 +160,7 @@ def test_tuned_geometries_are_all_bit_exact():
         for unroll in (1, 2, 4, 8):
             for cps in (0, 2):
                 geos.append(capi.Tune(kind=kind, threads=256, unroll=unroll, ctas_per_sm=cps, ld_hint=1, st_hint=1))
-        for ld in range(5):
+        for ld in range(6):
             for st in range(4):
                 geos.append(capi.Tune(kind=kind, threads=128, unroll=2, ctas_per_sm=0, ld_hint=ld, st_hint=st))
         for threads in (32, 64, 512, 1024):

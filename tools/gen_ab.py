@@ -1,11 +1,24 @@
 #!/usr/bin/env python
 """Short-list geometries for the interleaved A/B pass of b200va_tune."""
+import sys
+
 K1, K2, K3 = 2, 3, 4
+which = sys.argv[1] if len(sys.argv) > 1 else "round2"
 print("1 256 1 0 0 0 0 0 0")
-for kind in (K1, K3):
-    for threads, unroll in ((128, 1), (256, 1), (512, 1), (1024, 1), (128, 2), (256, 2), (512, 2), (1024, 2), (256, 4), (512, 4), (1024, 4), (256, 8)):
-        for ld, st in ((1, 1), (0, 0), (3, 3), (1, 0), (3, 0), (0, 1), (3, 1)):
-            print(kind, threads, unroll, 0, ld, st, 0, 0, 0)
-for threads, cps, stages, tile, mode in ((128, 1, 4, 8192, 0), (128, 2, 2, 8192, 0), (128, 1, 8, 4096, 0), (256, 1, 12, 4096, 1), (256, 1, 6, 16384, 1), (256, 1, 4, 8192, 0)):
-    for ld in (0, 3):
-        print(K2, threads, 0, cps, ld, 1, stages, tile, mode)
+if which == "round1":
+    for kind in (K1, K3):
+        for threads, unroll in ((128, 1), (256, 1), (512, 1), (1024, 1), (128, 2), (256, 2), (512, 2), (1024, 2), (256, 4), (512, 4), (1024, 4), (256, 8)):
+            for ld, st in ((1, 1), (0, 0), (3, 3), (1, 0), (3, 0), (0, 1), (3, 1)):
+                print(kind, threads, unroll, 0, ld, st, 0, 0, 0)
+    for threads, cps, stages, tile, mode in ((128, 1, 4, 8192, 0), (128, 2, 2, 8192, 0), (128, 1, 8, 4096, 0), (256, 1, 12, 4096, 1), (256, 1, 6, 16384, 1), (256, 1, 4, 8192, 0)):
+        for ld in (0, 3):
+            print(K2, threads, 0, cps, ld, 1, stages, tile, mode)
+else:
+    # round 2: thread counts around the winner, the L2::256B load hint, a few TMA shapes
+    for kind in (K1, K3):
+        for threads in (128, 192, 256, 320, 384, 448, 512, 576, 640, 768, 1024):
+            for unroll in (1, 2):
+                for ld, st in ((0, 1), (0, 0), (5, 1), (5, 0), (3, 0), (3, 1)):
+                    print(kind, threads, unroll, 0, ld, st, 0, 0, 0)
+    for threads, cps, stages, tile, mode in ((64, 2, 4, 8192, 0), (64, 4, 2, 8192, 0), (128, 1, 4, 8192, 0), (128, 2, 3, 8192, 0), (128, 1, 6, 8192, 0), (96, 2, 4, 8192, 0)):
+        print(K2, threads, 0, cps, 0, 1, stages, tile, mode)

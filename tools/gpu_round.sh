@@ -32,12 +32,12 @@ fi
 
 if has ab; then
   python tools/gen_ab.py > "$OUT/ab_geometries.txt"
-  for lg in 28 24 22 20; do
-    reps=20; [ $lg -le 24 ] && reps=200; [ $lg -le 20 ] && reps=1000
+  for lg in ${AB_SIZES:-28 26 25 24}; do
+    reps=20; [ $lg -le 26 ] && reps=80; [ $lg -le 24 ] && reps=200; [ $lg -le 20 ] && reps=1000
     timeout 900 $PKG/b200va_tune --n $((1<<lg)) --reps $reps --warmup 3 --rounds 7 < "$OUT/ab_geometries.txt" > "$OUT/ab_2p$lg.jsonl" 2> "$OUT/ab_2p$lg.err"
     echo "ab 2^$lg exit=$?" | tee -a "$OUT/status.txt"
   done
-  for lg in 28 24; do
+  for lg in ${AB_NOPDL_SIZES:-}; do
     reps=20; [ $lg -le 24 ] && reps=200
     B200VA_NO_PDL=1 timeout 900 $PKG/b200va_tune --n $((1<<lg)) --reps $reps --warmup 3 --rounds 7 < "$OUT/ab_geometries.txt" > "$OUT/ab_nopdl_2p$lg.jsonl" 2>> "$OUT/ab_2p$lg.err"
   done
@@ -91,6 +91,22 @@ if has cli; then
     timeout 600 ./vectorAdd --mode resident --n 2^24 --iters 5000 --graph 100 --json "../$OUT/cli_loop_graph.json" > /dev/null 2>> "../$OUT/cli.err"
     timeout 600 ./vectorAdd --mode staged --n 2^28 --iters 5 --json "../$OUT/cli_staged.json" > /dev/null 2>> "../$OUT/cli.err"
   )
+fi
+
+if has mgpu; then
+  G=${GPUS:-2}
+  nvidia-smi topo -m > "$OUT/topo.txt" 2>&1
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $G --steps 100 --warmup 5 > "$OUT/bench_${G}gpu.json" 2> "$OUT/bench_${G}gpu.err"; echo "bench ${G}gpu exit=$?" | tee -a "$OUT/status.txt"
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29512 \
+      bench.py --impl reference --gpus $G --steps 5 --warmup 1 > "$OUT/bench_reference_${G}gpu.json" 2>> "$OUT/bench_${G}gpu.err"
+  ( cd $PKG
+    timeout 600 ./vectorAdd --gpus $G --n 2^30 --iters 50 --json "../$OUT/cli_2p30_${G}gpu.json" > /dev/null 2>> "../$OUT/cli.err"; echo "cli 2^30 ${G}gpu exit=$?" | tee -a "../$OUT/status.txt"
+    timeout 600 ./vectorAdd --gpus $G --n 2^28 --iters 200 --json "../$OUT/cli_2p28_${G}gpu.json" > /dev/null 2>> "../$OUT/cli.err"
+    timeout 600 ./vectorAdd --gpus $G --n 1000000007 --iters 20 --json "../$OUT/cli_ragged_${G}gpu.json" > /dev/null 2>> "../$OUT/cli.err"
+    timeout 600 ./vectorAdd --gpus $G --mode staged --n 2^30 --iters 3 --json "../$OUT/cli_staged_2p30_${G}gpu.json" > /dev/null 2>> "../$OUT/cli.err"
+  )
+  cat "$OUT/bench_${G}gpu.json"
 fi
 
 if has ncu; then
