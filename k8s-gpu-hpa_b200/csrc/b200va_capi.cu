@@ -173,11 +173,12 @@ int ensure_smem_optin(tma_fn fn, int device, int bytes)
 
 // ----------------------------------------------------------------------- geometry
 // Production choices per size class, from the interleaved A/B sweeps on B200
-// (profiles/r01/b_ab_2p{20,22,24,28}.jsonl; median of 7 rounds of back-to-back launches):
-//   n >= 2^26  HBM streaming           K1 128-bit, 512 threads, 1 vector/thread, stores skip L1   7.25 TB/s @2^28
-//   2^23 < n   footprint a few x L2    K3 256-bit, 128 threads, L2 evict-first loads, plain stores 7.36 TB/s @2^24
-//   n <= 2^23  L2-resident             K1 128-bit, 256 threads x2, plain hints (let L2 keep it)    11.7 TB/s @2^22
-//   n <  2^21  launch-bound            K1 128-bit, 512 (>=2^19) / 128 threads x1
+// (profiles/r01/{b,c}_ab_2p*.jsonl; median of 7 rounds of back-to-back launches).  K_AUTO is
+// always the 128-bit kernel; thread count / unroll / cache hints follow the footprint:
+//   n >= 2^25       HBM streaming         512 thr x1, stores skip L1            7.23 TB/s @2^28, 7.14 @2^26, 7.00 @2^25
+//   2^23 < n < 2^25 footprint ~ 1-3 x L2  128 thr x2, L2 evict-first loads      7.33 TB/s @2^24
+//   2^21..2^23      L2-resident           256 thr x2, plain hints (L2 keeps it) 11.7 TB/s @2^22 (an L2 number)
+//   n < 2^21        launch-bound          512 thr (>= 2^19) / 128 thr, x1
 void default_tune(int variant, size_t n, b200va_tune_t* t)
 {
     std::memset(t, 0, sizeof *t);
@@ -216,10 +217,10 @@ void default_tune(int variant, size_t n, b200va_tune_t* t)
     }
     // B200VA_K_AUTO
     t->unroll = 1;
-    if (n >= (size_t{1} << 26)) {
+    if (n >= (size_t{1} << 25)) {
         t->kind = B200VA_K1_VEC128; t->threads = 512; t->ld_hint = LD_PLAIN; t->st_hint = ST_NA;
     } else if (n > (size_t{1} << 23)) {
-        t->kind = B200VA_K3_VEC256; t->threads = 128; t->ld_hint = LD_NA_EF; t->st_hint = ST_PLAIN;
+        t->kind = B200VA_K1_VEC128; t->threads = 128; t->unroll = 2; t->ld_hint = LD_NA_EF; t->st_hint = ST_PLAIN;
     } else if (n >= (size_t{1} << 21)) {
         t->kind = B200VA_K1_VEC128; t->threads = 256; t->unroll = 2; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
     } else if (n >= (size_t{1} << 19)) {
