@@ -167,6 +167,25 @@ int b200va_add_f32_host(const float *hA, const float *hB, float *hC, size_t n,
 int b200va_host_alloc(void **out, size_t bytes);
 int b200va_host_free(void *p);
 
+/* ---- generalised streaming element-wise core -------------------
+ * The tuned 128-bit streaming skeleton of the vectorAdd kernel over other element types
+ * and STREAM operations.  Not part of the reference's surface (its only op is the f32
+ * add, for which  b200va_stream(ADD, F32, ...)  is bit-identical to  b200va_add_f32).
+ *   COPY  c = a            SCALE c = s*a          ADD c = a + b      TRIAD c = fma(s, b, a)
+ * f32/f64: native IEEE arithmetic, round-to-nearest-even, no FTZ.  f16/bf16: operands
+ * widened exactly to f32, op in f32 (s rounded to f32), result rounded to nearest-even.
+ * dB is ignored (may be NULL) for COPY and SCALE.  Pointers aligned to the element size. */
+#define B200VA_OP_COPY   0
+#define B200VA_OP_SCALE  1
+#define B200VA_OP_ADD    2
+#define B200VA_OP_TRIAD  3
+#define B200VA_DT_F32    0
+#define B200VA_DT_F64    1
+#define B200VA_DT_F16    2
+#define B200VA_DT_BF16   3
+int b200va_stream(int op, int dtype, const void *dA, const void *dB, void *dC, size_t n,
+                  double scalar, void *stream);
+
 /* ---- shard arithmetic (8(e)): contiguous equal shards, starts on 16-byte multiples --- */
 int b200va_shard_range(size_t n, int world, int rank, size_t *begin, size_t *end);
 

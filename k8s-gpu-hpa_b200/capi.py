@@ -22,6 +22,8 @@ OK = 0
 ERR_INVALID, ERR_ALIGN, ERR_OVERLAP, ERR_VARIANT, ERR_NO_DEVICE, ERR_VERIFY, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 ERR_CUDA_BASE = -1000
 K_AUTO, K0_SCALAR, K1_VEC128, K2_TMA, K3_VEC256 = 0, 1, 2, 3, 4
+OPS = {"copy": 0, "scale": 1, "add": 2, "triad": 3}
+DTYPES = {"f32": 0, "f64": 1, "f16": 2, "bf16": 3}
 VARIANTS = {"auto": K_AUTO, "k0": K0_SCALAR, "k1": K1_VEC128, "k2": K2_TMA, "k3": K3_VEC256}
 
 
@@ -78,6 +80,7 @@ _SIGS = {
     "b200va_add_f32_host": (_I, [_P, _P, _P, _SZ, _I, _I]),
     "b200va_host_alloc": (_I, [C.POINTER(_P), _SZ]),
     "b200va_host_free": (_I, [_P]),
+    "b200va_stream": (_I, [_I, _I, _P, _P, _P, _SZ, C.c_double, _P]),
     "b200va_shard_range": (_I, [_SZ, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
 }
 for _name, (_res, _args) in _SIGS.items():

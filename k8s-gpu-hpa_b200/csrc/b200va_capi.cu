@@ -23,6 +23,7 @@
 
 #include "../../include/b200va.h"
 #include "b200va_kernels.cuh"
+#include "b200va_stream.cuh"
 
 using namespace b200va;
 
@@ -365,6 +366,62 @@ unsigned support_grid(const b200va_devinfo_t* di, size_t n, int threads)
 
 }  // namespace
 
+// ----------------------------------------------------------------------- f4 dispatch
+namespace {
+
+template <int DT, int OP>
+int launch_stream_typed(const void* dA, const void* dB, void* dC, size_t n, double scalar, cudaStream_t st)
+{
+    using S = typename dt_traits<DT>::scalar;
+    constexpr size_t ES = dt_traits<DT>::size;
+    constexpr bool binary = (OP == OP_ADD || OP == OP_TRIAD);
+    const S s = static_cast<S>(scalar);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dA), b = reinterpret_cast<uintptr_t>(dB),
+                    c = reinterpret_cast<uintptr_t>(dC);
+    const bool vec_ok = (a & 15u) == (c & 15u) && (!binary || (b & 15u) == (a & 15u));
+    if (!vec_ok) {
+        const size_t blocks = (n + 255) / 256;
+        if (blocks > 0x7fffffffull) return B200VA_ERR_INVALID;
+        stream_scalar<DT, OP><<<static_cast<unsigned>(blocks), 256, 0, st>>>(dA, dB, dC, n, s);
+        return cuda_err(cudaGetLastError());
+    }
+    size_t head = ((16u - (a & 15u)) & 15u) / ES;
+    if (head > n) head = n;
+    const size_t nvec = (n - head) * ES / 16;
+    // same footprint classes as the f32 add (default_tune), in 4-byte units
+    const size_t m = n * ES / 4;
+    unsigned threads = 128;
+    int unroll = 1;
+    bool skip_l1_stores = false;
+    if (m >= (size_t{1} << 25)) { threads = 512; skip_l1_stores = true; }
+    else if (m > (size_t{1} << 23)) { threads = 128; unroll = 2; }
+    else if (m >= (size_t{1} << 21)) { threads = 256; unroll = 2; }
+    else if (m >= (size_t{1} << 19)) { threads = 512; }
+    const size_t tile_vecs = static_cast<size_t>(threads) * unroll;
+    size_t grid = (nvec + tile_vecs - 1) / tile_vecs;
+    if (grid > 0x7fffffffull) grid = 0x7fffffffull;
+    if (grid == 0) grid = 1;
+    const size_t ntiles = (nvec + tile_vecs - 1) / tile_vecs;
+    using fn_t = void (*)(const void*, const void*, void*, size_t, size_t, size_t, size_t, S);
+    fn_t fn = skip_l1_stores ? (unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_NA> : stream_vec<DT, OP, 1, LD_PLAIN, ST_NA>)
+                             : (unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_PLAIN> : stream_vec<DT, OP, 1, LD_PLAIN, ST_PLAIN>);
+    return launch_kernel(fn, static_cast<unsigned>(grid), threads, 0, st, dA, dB, dC, n, head, nvec, ntiles, s);
+}
+
+template <int DT>
+int launch_stream_op(int op, const void* dA, const void* dB, void* dC, size_t n, double scalar, cudaStream_t st)
+{
+    switch (op) {
+        case OP_COPY:  return launch_stream_typed<DT, OP_COPY>(dA, dB, dC, n, scalar, st);
+        case OP_SCALE: return launch_stream_typed<DT, OP_SCALE>(dA, dB, dC, n, scalar, st);
+        case OP_ADD:   return launch_stream_typed<DT, OP_ADD>(dA, dB, dC, n, scalar, st);
+        case OP_TRIAD: return launch_stream_typed<DT, OP_TRIAD>(dA, dB, dC, n, scalar, st);
+    }
+    return B200VA_ERR_VARIANT;
+}
+
+}  // namespace
+
 // =============================================================================== ABI
 extern "C" {
 
@@ -649,6 +706,33 @@ int b200va_digest_f32(const float* d, size_t n, uint64_t* d_out, void* stream)
     reset_digest<<<1, 1, 0, st>>>(out);
     if (n) digest_bits<<<support_grid(di, n, 256), 256, 0, st>>>(d, n, out);
     return cuda_err(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ f4: STREAM-style ops
+int b200va_stream(int op, int dtype, const void* dA, const void* dB, void* dC, size_t n, double scalar, void* stream)
+{
+    if (op < 0 || op >= OP_COUNT || dtype < 0 || dtype >= DT_COUNT) return B200VA_ERR_VARIANT;
+    const b200va_devinfo_t* di = nullptr;
+    RC_TRY(current_dev_info(&di));
+    if (n == 0) return B200VA_OK;
+    const bool binary = (op == OP_ADD || op == OP_TRIAD);
+    if (!dA || !dC || (binary && !dB)) return B200VA_ERR_INVALID;
+    const size_t es = dtype == DT_F64 ? 8 : dtype == DT_F32 ? 4 : 2;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dA), b = reinterpret_cast<uintptr_t>(dB),
+                    c = reinterpret_cast<uintptr_t>(dC);
+    if (((a | c | (binary ? b : 0)) & (es - 1)) != 0) return B200VA_ERR_ALIGN;
+    if (n > (size_t{1} << 40)) return B200VA_ERR_INVALID;
+    const uintptr_t bytes = n * es;
+    auto partial = [&](uintptr_t x) { return x != c && x < c + bytes && c < x + bytes; };
+    if (partial(a) || (binary && partial(b))) return B200VA_ERR_OVERLAP;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case DT_F32:  return launch_stream_op<DT_F32>(op, dA, dB, dC, n, scalar, st);
+        case DT_F64:  return launch_stream_op<DT_F64>(op, dA, dB, dC, n, scalar, st);
+        case DT_F16:  return launch_stream_op<DT_F16>(op, dA, dB, dC, n, scalar, st);
+        case DT_BF16: return launch_stream_op<DT_BF16>(op, dA, dB, dC, n, scalar, st);
+    }
+    return B200VA_ERR_VARIANT;
 }
 
 // ------------------------------------------------------------------ shard arithmetic

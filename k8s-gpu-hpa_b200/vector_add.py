@@ -73,6 +73,27 @@ def add_loop(a, b, out, iters: int, *, graph_batch: int = 0, variant=K_AUTO, str
     return out
 
 
+_TORCH_DT = {"f32": "float32", "f64": "float64", "f16": "float16", "bf16": "bfloat16"}
+
+
+def stream(op: str, a, b=None, out=None, *, scalar: float = 0.0, stream=None):
+    """STREAM-style op (copy | scale | add | triad) on CUDA tensors of f32/f64/f16/bf16
+    through b200va_stream.  Asynchronous on the current stream."""
+    torch = _torch()
+    names = {getattr(torch, v): k for k, v in _TORCH_DT.items()}
+    if not a.is_cuda or a.dtype not in names or not a.is_contiguous():
+        raise TypeError("a must be a contiguous CUDA tensor of float32/float64/float16/bfloat16")
+    if out is None:
+        out = torch.empty_like(a)
+    for t in (b, out):
+        if t is not None and (t.dtype != a.dtype or t.numel() != a.numel() or not t.is_cuda or not t.is_contiguous()):
+            raise TypeError("operands must match a in dtype, length and device")
+    with torch.cuda.device(a.device):
+        check(lib.b200va_stream(capi.OPS[op], capi.DTYPES[names[a.dtype]], a.data_ptr(), b.data_ptr() if b is not None else None,
+                                out.data_ptr(), a.numel(), float(scalar), _stream_ptr(stream)), "b200va_stream")
+    return out
+
+
 def fill_ctr(out, seed: int, first: int = 0, *, stream=None):
     """Counter generator on the device: out[i] = ctr(seed, first + i)."""
     torch = _torch()

@@ -39,6 +39,11 @@ for _n, _r, _a in [
     ("oracle_fill_ctr_pair_mt", None, [_P, _P, _P, _SZ, _U64, _U64, _U64, _I]),
     ("oracle_vadd_digest_f32_mt", None, [_P, _P, _SZ, _I, _P]),
     ("oracle_time_vadd_mt", _I, [_SZ, _I, _I, _I, _P]),
+    ("oracle_stream", _I, [_I, _I, _P, _P, _P, _SZ, C.c_double]),
+    ("oracle_half_to_float", None, [_P, _P, _SZ]),
+    ("oracle_float_to_half", None, [_P, _P, _SZ]),
+    ("oracle_bf16_to_float", None, [_P, _P, _SZ]),
+    ("oracle_float_to_bf16", None, [_P, _P, _SZ]),
 ]:
     _f = getattr(_lib, _n)
     _f.restype, _f.argtypes = _r, _a
@@ -166,3 +171,65 @@ def time_vadd_mt(n: int, threads: int = 0, warmup: int = 1, reps: int = 5) -> li
     if rc != 0:
         raise MemoryError("oracle_time_vadd_mt: allocation failed")
     return list(secs)
+
+
+# ---------------------------------------------------------------- f4: STREAM-style ops
+OPS = {"copy": 0, "scale": 1, "add": 2, "triad": 3}
+DTYPES = {"f32": (0, np.float32), "f64": (1, np.float64), "f16": (2, np.uint16), "bf16": (3, np.uint16)}
+
+
+def stream(op: str, dtype: str, a: np.ndarray, b: np.ndarray | None, scalar: float = 0.0) -> np.ndarray:
+    """Oracle of b200va_stream. f16/bf16 arrays are uint16 bit patterns."""
+    code, npdt = DTYPES[dtype]
+    a = np.ascontiguousarray(a)
+    assert a.dtype == npdt, (a.dtype, npdt)
+    c = np.empty_like(a)
+    pb = np.ascontiguousarray(b).ctypes.data if b is not None else None
+    rc = _lib.oracle_stream(OPS[op], code, a.ctypes.data, pb, c.ctypes.data, a.size, float(scalar))
+    assert rc == 0
+    return c
+
+
+def half_to_float(h: np.ndarray) -> np.ndarray:
+    f = np.empty(h.size, np.float32)
+    _lib.oracle_half_to_float(np.ascontiguousarray(h).ctypes.data, f.ctypes.data, h.size)
+    return f
+
+
+def float_to_half(f: np.ndarray) -> np.ndarray:
+    h = np.empty(f.size, np.uint16)
+    _lib.oracle_float_to_half(np.ascontiguousarray(f, np.float32).ctypes.data, h.ctypes.data, f.size)
+    return h
+
+
+def bf16_to_float(h: np.ndarray) -> np.ndarray:
+    f = np.empty(h.size, np.float32)
+    _lib.oracle_bf16_to_float(np.ascontiguousarray(h).ctypes.data, f.ctypes.data, h.size)
+    return f
+
+
+def float_to_bf16(f: np.ndarray) -> np.ndarray:
+    h = np.empty(f.size, np.uint16)
+    _lib.oracle_float_to_bf16(np.ascontiguousarray(f, np.float32).ctypes.data, h.ctypes.data, f.size)
+    return h
+
+
+def first_mismatch_bits(x: np.ndarray, y: np.ndarray, dtype: str) -> int:
+    """First index where the bit patterns differ, NaNs (of the given dtype) matching as a class; -1 if none."""
+    x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+    if dtype == "f32":
+        ux, uy = x.view(np.uint32), y.view(np.uint32)
+        nx, ny = (ux & 0x7FFFFFFF) > 0x7F800000, (uy & 0x7FFFFFFF) > 0x7F800000
+    elif dtype == "f64":
+        ux, uy = x.view(np.uint64), y.view(np.uint64)
+        m, inf = np.uint64(0x7FFFFFFFFFFFFFFF), np.uint64(0x7FF0000000000000)
+        nx, ny = (ux & m) > inf, (uy & m) > inf
+    elif dtype == "f16":
+        ux, uy = x.view(np.uint16), y.view(np.uint16)
+        nx, ny = (ux & 0x7FFF) > 0x7C00, (uy & 0x7FFF) > 0x7C00
+    else:
+        ux, uy = x.view(np.uint16), y.view(np.uint16)
+        nx, ny = (ux & 0x7FFF) > 0x7F80, (uy & 0x7FFF) > 0x7F80
+    bad = (ux != uy) & ~(nx & ny)
+    idx = np.nonzero(bad)[0]
+    return int(idx[0]) if idx.size else -1

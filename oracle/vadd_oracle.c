@@ -353,3 +353,98 @@ int oracle_time_vadd_mt(size_t n, int threads, int warmup, int reps, double *sec
     free(a); free(b); free(c);
     return 0;
 }
+
+/* ============================================================================ f4 oracle
+ * STREAM-style ops of the generalised core (not in the reference,
+ * whose only operation is the f32 add above).  Semantics restated from include/b200va.h:
+ *   COPY c=a   SCALE c=s*a   ADD c=a+b   TRIAD c=fma(s,b,a)
+ * f32/f64 natively (RNE); f16/bf16: widen exactly to f32, op in f32 (s rounded to f32),
+ * round to nearest-even into the storage type.  The half conversions below are integer
+ * code written from the formats' definitions, independent of compiler half types. */
+static float half_to_float(uint16_t h)
+{
+    uint32_t s = (uint32_t)(h >> 15) << 31, e = (h >> 10) & 0x1f, m = h & 0x3ff, u;
+    if (e == 0x1f) u = s | 0x7f800000u | (m << 13);                 /* Inf / NaN */
+    else if (e) u = s | ((e + 112) << 23) | (m << 13);              /* normal: bias 15 -> 127 */
+    else if (m) {                                                   /* subnormal: renormalise */
+        int sh = 0;
+        while (!(m & 0x400)) { m <<= 1; ++sh; }
+        u = s | ((uint32_t)(113 - sh) << 23) | ((m & 0x3ff) << 13);
+    } else u = s;
+    float f; memcpy(&f, &u, 4); return f;
+}
+
+static uint16_t float_to_half_rne(float f)
+{
+    uint32_t u; memcpy(&u, &f, 4);
+    uint16_t s = (uint16_t)((u >> 16) & 0x8000);
+    uint32_t a = u & 0x7fffffffu;
+    if (a > 0x7f800000u) return (uint16_t)(s | 0x7fff);             /* NaN (class only) */
+    if (a >= 0x47800000u) return (uint16_t)(s | 0x7c00);            /* >= 65536 -> Inf (also Inf) */
+    int32_t e = (int32_t)(a >> 23) - 127;
+    uint32_t m = (a & 0x7fffffu) | 0x800000u;                       /* 24-bit significand */
+    int shift;                                                      /* bits to drop */
+    uint32_t base;
+    if (e >= -14) { shift = 13; base = (uint32_t)(e + 15) << 10; m &= 0x7fffffu; }
+    else { shift = 13 + (-14 - e); base = 0; if (shift > 25) return s; }   /* subnormal or zero */
+    uint32_t q = m >> shift, rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
+    uint32_t r = base + q;
+    if (rem > half || (rem == half && (r & 1))) r += 1;             /* carries ripple into the exponent */
+    return (uint16_t)(s | r);                                       /* 0x7c00 if it rounded up to Inf */
+}
+
+static float bf16_to_float(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+
+static uint16_t float_to_bf16_rne(float f)
+{
+    uint32_t u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x7fff);   /* NaN */
+    uint32_t lsb = (u >> 16) & 1;
+    u += 0x7fffu + lsb;                                             /* RNE; overflow rounds to Inf */
+    return (uint16_t)(u >> 16);
+}
+
+#include <math.h>
+enum { ORC_COPY = 0, ORC_SCALE = 1, ORC_ADD = 2, ORC_TRIAD = 3 };
+enum { ORC_F32 = 0, ORC_F64 = 1, ORC_F16 = 2, ORC_BF16 = 3 };
+
+static inline float stream_f32(int op, float a, float b, float s)
+{
+    switch (op) {
+        case ORC_SCALE: return s * a;
+        case ORC_ADD:   return a + b;
+        case ORC_TRIAD: return fmaf(s, b, a);
+        default:        return a;
+    }
+}
+
+/* Returns 0, or -1 for an unknown op/dtype. */
+int oracle_stream(int op, int dtype, const void *a, const void *b, void *c, size_t n, double scalar)
+{
+    if (op < 0 || op > 3 || dtype < 0 || dtype > 3) return -1;
+    const int binary = (op == ORC_ADD || op == ORC_TRIAD);
+    if (op == ORC_COPY) { memcpy(c, a, n * (dtype == ORC_F64 ? 8 : dtype == ORC_F32 ? 4 : 2)); return 0; }
+    if (dtype == ORC_F32) {
+        const float *x = (const float *)a, *y = (const float *)b; float *z = (float *)c; const float s = (float)scalar;
+        for (size_t i = 0; i < n; ++i) z[i] = stream_f32(op, x[i], binary ? y[i] : 0.f, s);
+    } else if (dtype == ORC_F64) {
+        const double *x = (const double *)a, *y = (const double *)b; double *z = (double *)c;
+        for (size_t i = 0; i < n; ++i)
+            z[i] = op == ORC_SCALE ? scalar * x[i] : op == ORC_ADD ? x[i] + y[i] : fma(scalar, y[i], x[i]);
+    } else {
+        const uint16_t *x = (const uint16_t *)a, *y = (const uint16_t *)b; uint16_t *z = (uint16_t *)c;
+        const float s = (float)scalar;
+        for (size_t i = 0; i < n; ++i) {
+            if (dtype == ORC_F16)
+                z[i] = float_to_half_rne(stream_f32(op, half_to_float(x[i]), binary ? half_to_float(y[i]) : 0.f, s));
+            else
+                z[i] = float_to_bf16_rne(stream_f32(op, bf16_to_float(x[i]), binary ? bf16_to_float(y[i]) : 0.f, s));
+        }
+    }
+    return 0;
+}
+
+void oracle_half_to_float(const uint16_t *h, float *f, size_t n) { for (size_t i = 0; i < n; ++i) f[i] = half_to_float(h[i]); }
+void oracle_float_to_half(const float *f, uint16_t *h, size_t n) { for (size_t i = 0; i < n; ++i) h[i] = float_to_half_rne(f[i]); }
+void oracle_bf16_to_float(const uint16_t *h, float *f, size_t n) { for (size_t i = 0; i < n; ++i) f[i] = bf16_to_float(h[i]); }
+void oracle_float_to_bf16(const float *f, uint16_t *h, size_t n) { for (size_t i = 0; i < n; ++i) h[i] = float_to_bf16_rne(f[i]); }

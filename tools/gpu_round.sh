@@ -93,9 +93,13 @@ if has cli; then
   )
 fi
 
+if has stream; then
+  timeout 900 python tools/stream_bench.py > "$OUT/stream_bench.jsonl" 2> "$OUT/stream_bench.err"; echo "stream bench exit=$?" | tee -a "$OUT/status.txt"
+fi
+
 if has mgpu; then
-  G=${GPUS:-2}
   nvidia-smi topo -m > "$OUT/topo.txt" 2>&1
+  for G in ${GPUS:-2}; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511 \
       bench.py --gpus $G --steps 100 --warmup 5 > "$OUT/bench_${G}gpu.json" 2> "$OUT/bench_${G}gpu.err"; echo "bench ${G}gpu exit=$?" | tee -a "$OUT/status.txt"
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29512 \
@@ -106,7 +110,8 @@ if has mgpu; then
     timeout 600 ./vectorAdd --gpus $G --n 1000000007 --iters 20 --json "../$OUT/cli_ragged_${G}gpu.json" > /dev/null 2>> "../$OUT/cli.err"
     timeout 600 ./vectorAdd --gpus $G --mode staged --n 2^30 --iters 3 --json "../$OUT/cli_staged_2p30_${G}gpu.json" > /dev/null 2>> "../$OUT/cli.err"
   )
-  cat "$OUT/bench_${G}gpu.json"
+  tail -1 "$OUT/bench_${G}gpu.json" | cut -c1-400
+  done
 fi
 
 if has ncu; then
