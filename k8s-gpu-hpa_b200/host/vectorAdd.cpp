@@ -545,9 +545,18 @@ int run_sharded(const Options& o)
         for (auto& r : res) for (int u : r.util_samples) if (u >= 0) { sum += u; ++cnt; mx = std::max(mx, u); }
         const double mean = cnt ? sum / cnt : 0.0;
         std::snprintf(buf, sizeof buf, ", \"nvml_util_mean\": %.1f, \"nvml_util_max\": %d, \"nvml_samples\": %d, "
-                      "\"hpa_threshold\": %.1f, \"hpa_would_scale\": %s", mean, mx, cnt, o.hpa_threshold,
-                      mean > o.hpa_threshold ? "true" : "false");
+                      "\"hpa_threshold\": %.1f, \"hpa_would_scale\": %s, \"nvml_sample_period_s\": 0.5, \"nvml_trace\": [",
+                      mean, mx, cnt, o.hpa_threshold, mean > o.hpa_threshold ? "true" : "false");
         js += buf;
+        for (size_t g = 0; g < res.size(); ++g) {          // one utilisation trace per GPU (0.5 s apart)
+            js += g ? ", [" : "[";
+            for (size_t i = 0; i < res[g].util_samples.size(); ++i) {
+                std::snprintf(buf, sizeof buf, "%s%d", i ? ", " : "", res[g].util_samples[i]);
+                js += buf;
+            }
+            js += "]";
+        }
+        js += "]";
     }
     if (o.cpu_baseline) {
         std::snprintf(buf, sizeof buf, ", \"cpu_baseline\": {\"n\": %zu, \"threads\": %d, \"ms_median\": %.3f, "

@@ -93,6 +93,10 @@ if has cli; then
   )
 fi
 
+if has hpa; then
+  timeout 900 python tools/hpa_trigger_replay.py 20 > "$OUT/hpa_trigger_replay.jsonl" 2> "$OUT/hpa_trigger_replay.err"; echo "hpa replay exit=$?" | tee -a "$OUT/status.txt"
+fi
+
 if has stream; then
   timeout 900 python tools/stream_bench.py > "$OUT/stream_bench.jsonl" 2> "$OUT/stream_bench.err"; echo "stream bench exit=$?" | tee -a "$OUT/status.txt"
 fi
