@@ -212,7 +212,8 @@ def run_ours(args) -> None:
     if not args.no_e2e:
         # pinned host buffers from the C ABI (pages on the GPU's NUMA node), filled from the
         # device arrays outside the timed region
-        pa, pb, pc = va.PinnedBuffer(n), va.PinnedBuffer(n), va.PinnedBuffer(n)
+        pa, pb, pc = va.PinnedBuffer(n, args.wc_inputs), va.PinnedBuffer(n, args.wc_inputs), va.PinnedBuffer(n)
+        host_nodes = [p.numa_node for p in (pa, pb, pc)]
         ha, hb, hc = (torch.from_numpy(p.array) for p in (pa, pb, pc))
         ha.copy_(a); hb.copy_(b)
         torch.cuda.synchronize()
@@ -236,7 +237,8 @@ def run_ours(args) -> None:
                "d2h_bytes_per_step": 4 * n * ws, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                "path": "b200va_stager_add_f32 " + ("zero-copy kernel over PCIe" if args.zero_copy else
                                                    "copy-engine pipeline: H2D(A,B) -> add -> D2H(C) per chunk"),
-               "host_memory": "pinned"}
+               "host_memory": "pinned" + (", write-combined inputs" if args.wc_inputs else ""),
+               "host_numa_nodes_rank0": host_nodes}
         del ha, hb, hc
         for p in (pa, pb, pc):
             p.free()
@@ -299,6 +301,7 @@ def main() -> None:
     ap.add_argument("--chunk-elems", type=int, default=0)
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--zero-copy", action="store_true")
+    ap.add_argument("--wc-inputs", action="store_true", help="write-combined pinned memory for the H2D sources")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

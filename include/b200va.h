@@ -163,9 +163,14 @@ int b200va_stager_destroy(b200va_stager_t *s);
 /* One-shot convenience: create, add, destroy (synchronous). */
 int b200va_add_f32_host(const float *hA, const float *hB, float *hC, size_t n,
                         int device, int variant);
-/* Pinned host memory for the pipeline (cudaHostAlloc / cudaFreeHost). */
+/* Pinned, mapped host memory for the pipeline (cudaHostAlloc / cudaFreeHost), placed on
+ * the NUMA node of the current CUDA device.  write_combined != 0 adds
+ * cudaHostAllocWriteCombined: meant for H2D *sources* the CPU only writes. */
 int b200va_host_alloc(void **out, size_t bytes);
+int b200va_host_alloc_ex(void **out, size_t bytes, int write_combined);
 int b200va_host_free(void *p);
+/* NUMA node that holds the page at p, or -1 if it cannot be determined. */
+int b200va_host_node_of(const void *p);
 
 /* ---- generalised streaming element-wise core -------------------
  * The tuned 128-bit streaming skeleton of the vectorAdd kernel over other element types

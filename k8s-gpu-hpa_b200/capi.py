@@ -79,7 +79,9 @@ _SIGS = {
     "b200va_stager_destroy": (_I, [_P]),
     "b200va_add_f32_host": (_I, [_P, _P, _P, _SZ, _I, _I]),
     "b200va_host_alloc": (_I, [C.POINTER(_P), _SZ]),
+    "b200va_host_alloc_ex": (_I, [C.POINTER(_P), _SZ, _I]),
     "b200va_host_free": (_I, [_P]),
+    "b200va_host_node_of": (_I, [_P]),
     "b200va_stream": (_I, [_I, _I, _P, _P, _P, _SZ, C.c_double, _P]),
     "b200va_shard_range": (_I, [_SZ, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
 }

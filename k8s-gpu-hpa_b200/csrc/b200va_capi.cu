@@ -247,6 +247,54 @@ int check_args(const float* dA, const float* dB, const float* dC, size_t n)
     return B200VA_OK;
 }
 
+// Launch geometry of a (validated) tune for a vector body of `nvec` vectors: the single
+// place grid/block/smem are computed -- used by launch() and reported by b200va_geometry().
+struct Geometry {
+    unsigned grid = 1, block = 0;
+    size_t smem = 0, ntiles = 0;
+};
+
+int plan_geometry(const b200va_tune_t& t, const b200va_devinfo_t* di, size_t n, size_t nvec, Geometry* g)
+{
+    if (t.kind == B200VA_K0_SCALAR) {
+        const size_t blocks = (n + 255) / 256;
+        if (blocks > 0x7fffffffull) return B200VA_ERR_INVALID;
+        g->grid = static_cast<unsigned>(blocks ? blocks : 1);
+        g->block = 256;
+        return B200VA_OK;
+    }
+    if (t.kind == B200VA_K2_TMA) {
+        if (t.threads < 32 || t.threads > 992 || (t.threads & 31)) return B200VA_ERR_VARIANT;
+        if (t.stages < 2 || t.stages > 32) return B200VA_ERR_VARIANT;
+        if (t.tile_bytes < 2048 || (t.tile_bytes & 2047)) return B200VA_ERR_VARIANT;
+        if (t.st_hint < 0 || t.st_hint >= ST_HINTS) return B200VA_ERR_VARIANT;
+        const long long smem = static_cast<long long>(t.stages) * 2 * t.tile_bytes + 16LL * t.stages;
+        if (smem > di->max_smem_optin) return B200VA_ERR_VARIANT;
+        g->smem = static_cast<size_t>(smem);
+        g->ntiles = (nvec * 16u + t.tile_bytes - 1) / t.tile_bytes;
+        size_t grid = static_cast<size_t>(di->sm_count) * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1);
+        if (grid > g->ntiles) grid = g->ntiles;
+        g->grid = static_cast<unsigned>(grid ? grid : 1);
+        g->block = static_cast<unsigned>(t.threads + 32);     // + the producer warp
+        return B200VA_OK;
+    }
+    if (t.kind != B200VA_K1_VEC128 && t.kind != B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
+    if (t.threads < 32 || t.threads > 1024 || (t.threads & 31)) return B200VA_ERR_VARIANT;
+    if (!is_pow2(t.unroll) || t.unroll > 8) return B200VA_ERR_VARIANT;
+    if (t.ld_hint < 0 || t.ld_hint >= LD_HINTS || t.st_hint < 0 || t.st_hint >= ST_HINTS) return B200VA_ERR_VARIANT;
+    const size_t tile_vecs = static_cast<size_t>(t.threads) * t.unroll;
+    g->ntiles = (nvec + tile_vecs - 1) / tile_vecs;
+    size_t grid = g->ntiles;
+    if (t.ctas_per_sm > 0) {
+        const size_t cap = static_cast<size_t>(di->sm_count) * t.ctas_per_sm;
+        if (grid > cap) grid = cap;
+    }
+    if (grid > 0x7fffffffull) grid = 0x7fffffffull;   // the kernel loops tile += gridDim.x
+    g->grid = static_cast<unsigned>(grid ? grid : 1);
+    g->block = static_cast<unsigned>(t.threads);
+    return B200VA_OK;
+}
+
 // All hot-path launches go through here: programmatic stream serialization lets launch
 // k+1 ramp up behind launch k's tail (the kernels call griddepcontrol.wait before their
 // first global access, so stream order is unchanged).  B200VA_NO_PDL=1 disables it.
@@ -306,53 +354,29 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
         if (t.kind == B200VA_K2_TMA) { vw = 0; break; }
         vw = (vw == 8) ? 4 : 0;
     }
+    Geometry g;
     if (vw == 0) {  // scalar control / mixed misalignment
-        const size_t blocks = (n + 255) / 256;
-        if (blocks > 0x7fffffffull) return B200VA_ERR_INVALID;
+        b200va_tune_t k0{};
+        k0.kind = B200VA_K0_SCALAR;
+        RC_TRY(plan_geometry(k0, di, n, 0, &g));
         // the control keeps the sample's plain launch (no programmatic dependent launch)
-        vadd_scalar<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(dA, dB, dC, n);
+        vadd_scalar<<<g.grid, g.block, 0, stream>>>(dA, dB, dC, n);
         return cuda_err(cudaGetLastError());
     }
     if (head > n) head = n;
     const size_t nvec = (n - head) / static_cast<size_t>(vw);
+    RC_TRY(plan_geometry(t, di, n, nvec, &g));
 
     if (t.kind == B200VA_K2_TMA) {
-        if (t.threads < 32 || t.threads > 992 || (t.threads & 31)) return B200VA_ERR_VARIANT;
-        if (t.stages < 2 || t.stages > 32) return B200VA_ERR_VARIANT;
-        if (t.tile_bytes < 2048 || (t.tile_bytes & 2047)) return B200VA_ERR_VARIANT;
-        if (t.st_hint < 0 || t.st_hint >= ST_HINTS) return B200VA_ERR_VARIANT;
-        const long long smem = static_cast<long long>(t.stages) * 2 * t.tile_bytes + 16LL * t.stages;
-        if (smem > di->max_smem_optin) return B200VA_ERR_VARIANT;
-        const bool hint = (t.ld_hint == LD_NA_EF);
-        tma_fn fn = pick_tma(t.store_mode, hint, t.st_hint);
+        tma_fn fn = pick_tma(t.store_mode, t.ld_hint == LD_NA_EF, t.st_hint);
         if (!fn) return B200VA_ERR_VARIANT;
-        RC_TRY(ensure_smem_optin(fn, di->device, static_cast<int>(smem)));
-        const size_t ntiles = (nvec * 16u + t.tile_bytes - 1) / t.tile_bytes;
-        size_t grid = static_cast<size_t>(di->sm_count) * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1);
-        if (grid > ntiles) grid = ntiles;
-        if (grid == 0) grid = 1;
-        return launch_kernel(fn, static_cast<unsigned>(grid), static_cast<unsigned>(t.threads + 32),
-                             static_cast<size_t>(smem), stream, dA, dB, dC, n, head, nvec,
+        RC_TRY(ensure_smem_optin(fn, di->device, static_cast<int>(g.smem)));
+        return launch_kernel(fn, g.grid, g.block, g.smem, stream, dA, dB, dC, n, head, nvec,
                              static_cast<uint32_t>(t.tile_bytes), static_cast<uint32_t>(t.stages));
     }
-
-    if (t.threads < 32 || t.threads > 1024 || (t.threads & 31)) return B200VA_ERR_VARIANT;
-    if (!is_pow2(t.unroll) || t.unroll > 8) return B200VA_ERR_VARIANT;
-    if (t.ld_hint < 0 || t.ld_hint >= LD_HINTS || t.st_hint < 0 || t.st_hint >= ST_HINTS)
-        return B200VA_ERR_VARIANT;
     vec_fn fn = pick_vec(vw, t.unroll, t.ld_hint, t.st_hint);
     if (!fn) return B200VA_ERR_VARIANT;
-    const size_t tile_vecs = static_cast<size_t>(t.threads) * t.unroll;
-    const size_t ntiles = (nvec + tile_vecs - 1) / tile_vecs;
-    size_t grid = ntiles;
-    if (t.ctas_per_sm > 0) {
-        const size_t cap = static_cast<size_t>(di->sm_count) * t.ctas_per_sm;
-        if (grid > cap) grid = cap;
-    }
-    if (grid > 0x7fffffffull) grid = 0x7fffffffull;   // kernel loops tile += gridDim.x
-    if (grid == 0) grid = 1;
-    return launch_kernel(fn, static_cast<unsigned>(grid), static_cast<unsigned>(t.threads), 0, stream, dA, dB, dC,
-                         n, head, nvec, ntiles);
+    return launch_kernel(fn, g.grid, g.block, 0, stream, dA, dB, dC, n, head, nvec, g.ntiles);
 }
 
 unsigned support_grid(const b200va_devinfo_t* di, size_t n, int threads)
@@ -465,32 +489,12 @@ int b200va_geometry(const b200va_tune_t* tune, size_t n, int device, unsigned* g
     if (!tune || !grid || !block) return B200VA_ERR_INVALID;
     const b200va_devinfo_t* di = nullptr;
     RC_TRY(dev_info(device, &di));
-    b200va_tune_t t = *tune;
-    unsigned smem = 0;
-    if (t.kind == B200VA_K0_SCALAR) {
-        *grid = static_cast<unsigned>((n + 255) / 256);
-        *block = 256;
-    } else if (t.kind == B200VA_K2_TMA) {
-        const size_t nvec = n / 4;
-        const size_t ntiles = (nvec * 16u + t.tile_bytes - 1) / (t.tile_bytes ? t.tile_bytes : 1);
-        size_t g = static_cast<size_t>(di->sm_count) * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1);
-        if (g > ntiles) g = ntiles;
-        *grid = static_cast<unsigned>(g ? g : 1);
-        *block = static_cast<unsigned>(t.threads + 32);
-        smem = static_cast<unsigned>(t.stages * 2 * t.tile_bytes + 16 * t.stages);
-    } else if (t.kind == B200VA_K1_VEC128 || t.kind == B200VA_K3_VEC256) {
-        const size_t vw = t.kind == B200VA_K3_VEC256 ? 8 : 4;
-        const size_t tile_vecs = static_cast<size_t>(t.threads) * (t.unroll ? t.unroll : 1);
-        size_t g = (n / vw + tile_vecs - 1) / (tile_vecs ? tile_vecs : 1);
-        if (t.ctas_per_sm > 0 && g > static_cast<size_t>(di->sm_count) * t.ctas_per_sm)
-            g = static_cast<size_t>(di->sm_count) * t.ctas_per_sm;
-        if (g > 0x7fffffffull) g = 0x7fffffffull;
-        *grid = static_cast<unsigned>(g ? g : 1);
-        *block = static_cast<unsigned>(t.threads);
-    } else {
-        return B200VA_ERR_VARIANT;
-    }
-    if (dyn_smem_bytes) *dyn_smem_bytes = smem;
+    Geometry g;
+    const size_t vw = tune->kind == B200VA_K3_VEC256 ? 8 : 4;
+    RC_TRY(plan_geometry(*tune, di, n, n / vw, &g));
+    *grid = g.grid;
+    *block = g.block;
+    if (dyn_smem_bytes) *dyn_smem_bytes = static_cast<unsigned>(g.smem);
     return B200VA_OK;
 }
 
@@ -808,7 +812,7 @@ static bool node_cpuset(int node, const cpu_set_t& allowed, cpu_set_t* out)
 // the calling thread is moved onto that node's CPUs (and its memory policy set to prefer
 // the node) for the duration of the allocation, so the first touch inside cudaHostAlloc
 // lands there; a PCIe DMA then never crosses the inter-socket link.
-int b200va_host_alloc(void** out, size_t bytes)
+int b200va_host_alloc_ex(void** out, size_t bytes, int write_combined)
 {
     if (!out) return B200VA_ERR_INVALID;
     const int node = device_numa_node();
@@ -821,11 +825,24 @@ int b200va_host_alloc(void** out, size_t bytes)
             policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0;
         }
     }
-    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped);
+    unsigned flags = cudaHostAllocPortable | cudaHostAllocMapped;
+    if (write_combined) flags |= cudaHostAllocWriteCombined;   // H2D sources only: CPU reads of WC memory crawl
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, flags);
     if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
     if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
     CU_TRY(e);
     return B200VA_OK;
+}
+
+int b200va_host_alloc(void** out, size_t bytes) { return b200va_host_alloc_ex(out, bytes, 0); }
+
+// NUMA node holding the page at `p` (get_mempolicy(MPOL_F_NODE | MPOL_F_ADDR)), or -1.
+int b200va_host_node_of(const void* p)
+{
+    int node = -1;
+    if (!p) return -1;
+    if (syscall(SYS_get_mempolicy, &node, nullptr, 0ul, const_cast<void*>(p), 3ul /* F_NODE|F_ADDR */) != 0) return -1;
+    return node;
 }
 
 int b200va_host_free(void* p)

@@ -165,11 +165,16 @@ class PinnedBuffer:
     """Pinned, GPU-local-NUMA host memory from b200va_host_alloc, viewed as a float32 numpy
     array (``.array``).  The memory lives until ``free()`` / garbage collection."""
 
-    def __init__(self, n: int):
+    def __init__(self, n: int, write_combined: bool = False):
         self._p = C.c_void_p()
         self.n = n
-        check(lib.b200va_host_alloc(C.byref(self._p), max(1, n) * 4), "b200va_host_alloc")
+        check(lib.b200va_host_alloc_ex(C.byref(self._p), max(1, n) * 4, 1 if write_combined else 0), "b200va_host_alloc_ex")
         self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_float)), shape=(n,))
+
+    @property
+    def numa_node(self) -> int:
+        """NUMA node of the first page (-1 if unknown)."""
+        return int(lib.b200va_host_node_of(self._p)) if self._p else -1
 
     def free(self):
         if self._p:

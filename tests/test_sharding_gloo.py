@@ -66,6 +66,6 @@ def test_two_rank_shards_combine_to_the_unsharded_answer(n):
 def test_single_process_fallbacks():
     from k8s_gpu_hpa_b200 import sharding
 
-    assert sharding.init("gloo") is False or True
+    assert sharding.init("gloo") is False          # no torchrun environment: stays single-process
     assert sharding.max_over_ranks(3.5) == 3.5
     assert sharding.combine_digests((5, 7)) == (5, 7)

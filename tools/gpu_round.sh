@@ -93,6 +93,19 @@ if has cli; then
   )
 fi
 
+if has e2ex; then
+  for G in ${GPUS:-1 4}; do
+    i=0
+    for opt in "" "--wc-inputs" "--zero-copy" "--zero-copy --wc-inputs" "--chunk-elems 16777216 --depth 2"; do
+      i=$((i+1))
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port $((29520+i)) \
+          bench.py --gpus $G --steps 20 --warmup 3 --e2e-steps 6 --no-cpu-baseline $opt 2>> "$OUT/e2ex.err" | tail -1 | \
+          python -c "import sys,json; d=json.loads(sys.stdin.read()); print(json.dumps({'gpus': $G, 'opt': '$opt', 'e2e': d['e2e']}))" >> "$OUT/e2ex.jsonl"
+    done
+  done
+  cat "$OUT/e2ex.jsonl"
+fi
+
 if has hpa; then
   timeout 900 python tools/hpa_trigger_replay.py 20 > "$OUT/hpa_trigger_replay.jsonl" 2> "$OUT/hpa_trigger_replay.err"; echo "hpa replay exit=$?" | tee -a "$OUT/status.txt"
 fi
