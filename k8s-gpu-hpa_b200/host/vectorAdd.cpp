@@ -96,6 +96,18 @@ int host_cpus()
     return c > 0 ? static_cast<int>(c) : 1;
 }
 
+// Container CPU bandwidth quota in CPUs (cgroup v2 cpu.max), 0 if unlimited/unknown.
+double cpu_quota()
+{
+    FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (!f) return 0.0;
+    char q[64];
+    double period = 0;
+    const int got = std::fscanf(f, "%63s %lf", q, &period);
+    std::fclose(f);
+    return (got == 2 && std::strcmp(q, "max") != 0 && period > 0) ? std::atof(q) / period : 0.0;
+}
+
 int parse_variant(const char* s)
 {
     if (!std::strcmp(s, "auto")) return B200VA_K_AUTO;
@@ -201,7 +213,11 @@ struct CpuBaseline { double elems_per_s = 0, gbps = 0, ms_median = 0; int thread
 CpuBaseline run_cpu_baseline(size_t n, int threads)
 {
     CpuBaseline r;
-    if (threads <= 0) threads = host_cpus();
+    if (threads <= 0) {   // more runnable threads than ~2x the cgroup quota only get throttled
+        threads = host_cpus();
+        const double q = cpu_quota();
+        if (q > 0) threads = std::max(1, std::min(threads, static_cast<int>(2 * q + 0.5)));
+    }
     r.threads = threads;
     r.n = n;
     float *a = nullptr, *b = nullptr, *c = nullptr;

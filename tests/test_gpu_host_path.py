@@ -86,3 +86,18 @@ def test_cli_staged_mode_and_duty_cycle():
     assert p.returncode == 0, p.stderr
     r = json.loads(p.stdout.strip().splitlines()[-1])
     assert r["mismatches"] == 0 and 0.0 < r["gpu_busy_frac"] < 0.9
+
+
+@pytest.mark.parametrize("gpus", [2, 4, 8])
+def test_cli_shards_across_gpus(gpus):
+    """BASELINE.json configs[2] shape on however many GPUs the box has: contiguous shards, no
+    collective, digest identical to the unsharded oracle."""
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    n = (1 << 26) + 12345
+    p = va.run_cli("--gpus", str(gpus), "--n", str(n), "--iters", "10")
+    assert p.returncode == 0, p.stderr
+    r = json.loads(p.stdout.strip().splitlines()[-1])
+    s, x = oracle.ctr_vadd_digest(n)
+    assert r["gpus"] == gpus and r["mismatches"] == 0
+    assert int(r["digest_sum"], 16) == s and int(r["digest_xor"], 16) == x
