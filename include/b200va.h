@@ -69,7 +69,8 @@ typedef struct b200va_tune {
     int st_hint;      /* 0 plain, 1 L1::no_allocate,   2 .cs, 3 no_allocate+L2 evict_first */
     int stages;       /* TMA: ring depth (2..16)                                        */
     int tile_bytes;   /* TMA: bytes per array per stage (multiple of 2048)              */
-    int store_mode;   /* TMA: 0 = st.global from registers, 1 = bulk store from smem    */
+    int store_mode;   /* TMA: 0 = st.global from registers, 1 = bulk store from smem,
+                         2 = register stores + cluster-launch-control tile scheduler    */
 } b200va_tune_t;
 
 typedef struct b200va_devinfo {

@@ -142,8 +142,22 @@ tma_fn pick_tma_st(int st)
     return nullptr;
 }
 
+template <bool HINT>
+tma_fn pick_tma_clc_st(int st)
+{
+    switch (st) {
+        case ST_PLAIN: return vadd_tma_clc<HINT, ST_PLAIN>;
+        case ST_NA:    return vadd_tma_clc<HINT, ST_NA>;
+        case ST_CS:    return vadd_tma_clc<HINT, ST_CS>;
+        case ST_NA_EF: return vadd_tma_clc<HINT, ST_NA_EF>;
+    }
+    return nullptr;
+}
+
 tma_fn pick_tma(int store_mode, bool l2_hint, int st)
 {
+    if (store_mode == 2)  // cluster-launch-control tile scheduler, register stores
+        return l2_hint ? pick_tma_clc_st<true>(st) : pick_tma_clc_st<false>(st);
     if (store_mode == 1)  // st hint is meaningless for bulk stores: one instantiation
         return l2_hint ? vadd_tma<1, true, ST_PLAIN> : vadd_tma<1, false, ST_PLAIN>;
     return l2_hint ? pick_tma_st<0, true>(st) : pick_tma_st<0, false>(st);
@@ -268,11 +282,16 @@ int plan_geometry(const b200va_tune_t& t, const b200va_devinfo_t* di, size_t n, 
         if (t.stages < 2 || t.stages > 32) return B200VA_ERR_VARIANT;
         if (t.tile_bytes < 2048 || (t.tile_bytes & 2047)) return B200VA_ERR_VARIANT;
         if (t.st_hint < 0 || t.st_hint >= ST_HINTS) return B200VA_ERR_VARIANT;
-        const long long smem = static_cast<long long>(t.stages) * 2 * t.tile_bytes + 16LL * t.stages;
+        if (t.store_mode < 0 || t.store_mode > 2) return B200VA_ERR_VARIANT;
+        // ring + full/empty barriers; the CLC form adds a barrier, a 16-B response and a tile slot per stage
+        const long long smem = static_cast<long long>(t.stages) * 2 * t.tile_bytes +
+                               (t.store_mode == 2 ? 44LL * t.stages + 16 : 16LL * t.stages);
         if (smem > di->max_smem_optin) return B200VA_ERR_VARIANT;
         g->smem = static_cast<size_t>(smem);
         g->ntiles = (nvec * 16u + t.tile_bytes - 1) / t.tile_bytes;
         size_t grid = static_cast<size_t>(di->sm_count) * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1);
+        if (t.store_mode == 2) grid = g->ntiles;          // one CTA per tile; resident CTAs cancel the rest
+        if (grid > 0x7fffffffull) return B200VA_ERR_INVALID;
         if (grid > g->ntiles) grid = g->ntiles;
         g->grid = static_cast<unsigned>(grid ? grid : 1);
         g->block = static_cast<unsigned>(t.threads + 32);     // + the producer warp

@@ -247,6 +247,149 @@ vadd_tma(const float* A, const float* B, float* C, size_t n, size_t head, size_t
     }
 }
 
+// ------------------------------------------------------------------------------ K2c
+// The TMA ring with Blackwell's cluster-launch-control tile scheduler.  The grid has one
+// CTA per tile, but only as many CTAs as fit are ever resident: each resident CTA's
+// producer lane, besides streaming its own tile through the ring, keeps `stages`
+// try_cancel requests in flight; every success hands it the index of a CTA that has not
+// started yet, whose tile it then loads into the next free stage.  Work is therefore
+// balanced dynamically across SMs (a static persistent split costs ~10 % here because the
+// SMs do not all see the same memory latency) while the ring, the barriers and the CTA
+// stay alive.  Consumers learn each stage's tile index from shared memory; a sentinel
+// ends them.  Register stores only (STORE_MODE 0 of vadd_tma).
+template <bool L2_HINT, int ST>
+__global__ void __launch_bounds__(1024, 1)
+vadd_tma_clc(const float* A, const float* B, float* C, size_t n, size_t head, size_t nvec4,
+             uint32_t tile_bytes, uint32_t stages)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + stages * 2u * tile_bytes;       // full[], empty[], clc_bar[]
+    const uint32_t clc_base = (bar_base + 3u * stages * 8u + 15u) & ~15u; // 16-byte aligned responses
+    const uint32_t slot_base = clc_base + stages * 16u;                   // uint32 tile index per stage
+    const uint32_t n_cons = blockDim.x - 32u;
+    const uint32_t n_cons_warps = n_cons >> 5;
+    constexpr uint32_t kDone = 0xffffffffu;
+
+    auto full_bar = [&](uint32_t s) { return bar_base + s * 8u; };
+    auto empty_bar = [&](uint32_t s) { return bar_base + (stages + s) * 8u; };
+    auto clc_bar = [&](uint32_t s) { return bar_base + (2u * stages + s) * 8u; };
+    auto clc_resp = [&](uint32_t s) { return clc_base + s * 16u; };
+    auto tile_a = [&](uint32_t s) { return smem_base + s * 2u * tile_bytes; };
+    auto tile_b = [&](uint32_t s) { return smem_base + s * 2u * tile_bytes + tile_bytes; };
+    volatile uint32_t* tile_slot = reinterpret_cast<volatile uint32_t*>(smem + (slot_base - smem_base));
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < stages; ++s) {
+            mbar_init(full_bar(s), 1u);
+            mbar_init(empty_bar(s), n_cons_warps);
+            mbar_init(clc_bar(s), 1u);
+        }
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+
+    const unsigned char* a = reinterpret_cast<const unsigned char*>(A + head);
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(B + head);
+    unsigned char* c = reinterpret_cast<unsigned char*>(C + head);
+    const size_t body_bytes = nvec4 * 16u;
+
+    uint64_t pol = 0;
+    if constexpr (L2_HINT || ST == ST_NA_EF) pol = l2_evict_first_policy();
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+            // ---------------------------------------------------- producer + scheduler
+            for (uint32_t j = 0; j < stages; ++j) {               // `stages` requests in flight
+                mbar_arrive_expect_tx(clc_bar(j), 16u);
+                clc_try_cancel(clc_resp(j), clc_bar(j));
+            }
+            uint32_t outstanding = stages, consumed = 0;
+            bool failed = false;
+            uint32_t tile = blockIdx.x, s = 0, ph = 0;
+            while (body_bytes != 0) {                             // (n < 4: only the scalar edges exist)
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const size_t off = static_cast<size_t>(tile) * tile_bytes;
+                const size_t left = body_bytes - off;
+                const uint32_t bytes = left < tile_bytes ? static_cast<uint32_t>(left) : tile_bytes;
+                tile_slot[s] = tile;                              // published by the arrive below (release)
+                mbar_arrive_expect_tx(full_bar(s), 2u * bytes);
+                bulk_g2s<L2_HINT>(tile_a(s), a + off, bytes, full_bar(s), pol);
+                bulk_g2s<L2_HINT>(tile_b(s), b + off, bytes, full_bar(s), pol);
+                if (++s == stages) { s = 0; ph ^= 1u; }
+
+                // next tile: the oldest outstanding response; after the first failure nothing
+                // is re-armed, but every outstanding response is still drained before exit
+                bool have_next = false;
+                while (outstanding > 0 && !have_next) {
+                    const uint32_t j = consumed % stages;
+                    mbar_wait(clc_bar(j), (consumed / stages) & 1u);
+                    uint32_t next = 0;
+                    const bool ok = clc_query(clc_resp(j), next);
+                    ++consumed;
+                    --outstanding;
+                    if (ok) {
+                        tile = next;
+                        have_next = true;
+                        if (!failed) {
+                            mbar_arrive_expect_tx(clc_bar(j), 16u);
+                            clc_try_cancel(clc_resp(j), clc_bar(j));
+                            ++outstanding;
+                        }
+                    } else {
+                        failed = true;
+                    }
+                }
+                if (!have_next) break;
+            }
+            while (outstanding > 0) {                             // (only reached with requests left when n < 4)
+                mbar_wait(clc_bar(consumed % stages), (consumed / stages) & 1u);
+                ++consumed;
+                --outstanding;
+            }
+            mbar_wait(empty_bar(s), ph ^ 1u);                     // sentinel: no more tiles
+            tile_slot[s] = kDone;
+            mbar_arrive(full_bar(s));
+        }
+    } else {
+        // ------------------------------------------------------------ consumers
+        const uint32_t ct = threadIdx.x - 32u;
+        uint32_t s = 0, ph = 0;
+        while (true) {
+            mbar_wait(full_bar(s), ph);
+            const uint32_t tile = tile_slot[s];
+            if (tile == kDone) break;
+            const size_t off = static_cast<size_t>(tile) * tile_bytes;
+            const size_t left = body_bytes - off;
+            const uint32_t bytes = left < tile_bytes ? static_cast<uint32_t>(left) : tile_bytes;
+            const uint32_t nv = bytes >> 4;
+            const uint32_t sa = tile_a(s), sb = tile_b(s);
+            float* cg = reinterpret_cast<float*>(c + off);
+
+            uint32_t v = ct;
+            for (; v + 3u * n_cons < nv; v += 4u * n_cons) {
+                f32x4 x[4], y[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = lds128(sa + (v + j * n_cons) * 16u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[j] = lds128(sb + (v + j * n_cons) * 16u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) stg128<ST>(cg + (v + j * n_cons) * 4u, add_vec(x[j], y[j]), pol);
+            }
+            for (; v < nv; v += n_cons)
+                stg128<ST>(cg + v * 4u, add_vec(lds128(sa + v * 16u), lds128(sb + v * 16u)), pol);
+
+            __syncwarp();
+            if ((threadIdx.x & 31u) == 0) mbar_arrive(empty_bar(s));
+            if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+        if (blockIdx.x == 0) add_edges(A, B, C, n, head, head + nvec4 * 4u, ct);
+    }
+}
+
 // ---------------------------------------------------------------- support kernels
 __device__ __forceinline__ uint64_t splitmix64(uint64_t z)
 {

@@ -268,6 +268,39 @@ __device__ __forceinline__ void pdl_wait()
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- cluster launch control
+// Blackwell's hardware work-stealing for persistent kernels (PTX 8.6, sm_100): a running
+// CTA asks to cancel the launch of a not-yet-started CTA of the same grid and, on success,
+// receives that CTA's index and does its work.  The 16-byte response lands in shared
+// memory through the async proxy and completes 16 bytes on an mbarrier.
+__device__ __forceinline__ void clc_try_cancel(uint32_t response_smem, uint32_t bar)
+{
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                 :: "r"(response_smem), "r"(bar) : "memory");
+}
+
+// Decodes a response: returns true and the cancelled CTA's blockIdx.x if the request
+// succeeded; false if there was nothing left to cancel (the index is then undefined).
+__device__ __forceinline__ bool clc_query(uint32_t response_smem, uint32_t& ctaid_x)
+{
+    uint64_t lo, hi;
+    uint32_t ok, x;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(response_smem) : "memory");
+    asm volatile(
+        "{\n"
+        ".reg .b128 resp;\n"
+        ".reg .pred p;\n"
+        "mov.b128 resp, {%2, %3};\n"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, resp;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "mov.b32 %1, 0;\n"
+        "@p clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %1, resp;\n"
+        "}\n"
+        : "=r"(ok), "=r"(x) : "l"(lo), "l"(hi));
+    ctaid_x = x;
+    return ok != 0;
+}
+
 // Named barrier over a subset of the CTA's warps (id 1..15; 0 is __syncthreads).
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
 {

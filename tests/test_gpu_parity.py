@@ -172,11 +172,43 @@ def test_tuned_geometries_are_all_bit_exact():
                     geos.append(capi.Tune(kind=capi.K2_TMA, threads=threads, ctas_per_sm=1, ld_hint=ld, st_hint=1,
                                           stages=stages, tile_bytes=tile, store_mode=mode))
         geos.append(capi.Tune(kind=capi.K2_TMA, threads=256, ctas_per_sm=2, stages=3, tile_bytes=16384, store_mode=mode))
+    for stages, tile in ((2, 2048), (3, 8192), (4, 8192), (5, 4096), (6, 16384), (4, 28672)):      # CLC tile scheduler
+        for threads in (32, 128, 512):
+            geos.append(capi.Tune(kind=capi.K2_TMA, threads=threads, ld_hint=0, st_hint=1, stages=stages, tile_bytes=tile,
+                                  store_mode=2))
     for t in geos:
         out = torch.full((n,), -1.0, dtype=torch.float32, device="cuda")
         va.add(a, b, out, tune=t)
         torch.cuda.synchronize()
         assert_bits_equal(out, want, str(t.as_dict()))
+
+
+def test_clc_scheduled_tma_kernel_ragged_sizes_and_offsets():
+    """store_mode 2: one CTA per tile, resident CTAs steal the rest through cluster launch
+    control -- every tile must be processed exactly once whatever the tile count."""
+    nmax = max(SIZES)
+    ha, hb = oracle.fill_ctr(nmax + 8, 0x0A, 77), oracle.fill_ctr(nmax + 8, 0x0B, 77)
+    a, b = dev(ha), dev(hb)
+    for t in (capi.Tune(kind=capi.K2_TMA, threads=128, st_hint=1, stages=4, tile_bytes=8192, store_mode=2),
+              capi.Tune(kind=capi.K2_TMA, threads=64, st_hint=0, stages=3, tile_bytes=2048, store_mode=2)):
+        for n in SIZES:
+            for off in (0, 1, 3):
+                out = torch.full((n + 16,), -3.0, dtype=torch.float32, device="cuda")
+                va.add(a[off:off + n], b[off:off + n], out[off:off + n] if off + n <= n + 16 else out[:n], tune=t)
+                torch.cuda.synchronize()
+                got = out[off:off + n] if off + n <= n + 16 else out[:n]
+                assert_bits_equal(got, oracle.vadd(ha[off:off + n].copy(), hb[off:off + n].copy()), f"clc n={n} off={off}")
+    # back-to-back launches (PDL chain) keep producing the same bits
+    n = 1 << 24
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    y = torch.empty_like(x)
+    z = torch.empty_like(x)
+    va.fill_ctr(x, 0x0A)
+    va.fill_ctr(y, 0x0B)
+    t = capi.Tune(kind=capi.K2_TMA, threads=128, st_hint=1, stages=4, tile_bytes=8192, store_mode=2)
+    for _ in range(50):
+        va.add(x, y, z, tune=t)
+    assert va.digest(z) == oracle.ctr_vadd_digest(n) and va.verify(x, y, z) == (0, -1)
 
 
 def test_device_verify_and_digest_detect_a_single_flipped_bit():

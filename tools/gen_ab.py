@@ -13,6 +13,15 @@ if which == "round1":
     for threads, cps, stages, tile, mode in ((128, 1, 4, 8192, 0), (128, 2, 2, 8192, 0), (128, 1, 8, 4096, 0), (256, 1, 12, 4096, 1), (256, 1, 6, 16384, 1), (256, 1, 4, 8192, 0)):
         for ld in (0, 3):
             print(K2, threads, 0, cps, ld, 1, stages, tile, mode)
+elif which == "clc":
+    print(K1, 512, 1, 0, 0, 1, 0, 0, 0)
+    print(K3, 768, 2, 0, 0, 1, 0, 0, 0)
+    print(K2, 128, 0, 1, 0, 1, 4, 8192, 0)
+    for threads in (64, 128, 256, 512):
+        for stages, tile in ((2, 8192), (3, 8192), (4, 8192), (6, 8192), (8, 8192), (2, 16384), (3, 16384), (4, 16384), (6, 16384),
+                             (4, 4096), (8, 4096), (2, 32768), (3, 32768), (12, 8192), (6, 32768)):
+            for ld, st in ((0, 1), (3, 1), (0, 0)):
+                print(K2, threads, 0, 1, ld, st, stages, tile, 2)
 else:
     # round 2: thread counts around the winner, the L2::256B load hint, a few TMA shapes
     for kind in (K1, K3):

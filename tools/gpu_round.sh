@@ -31,7 +31,7 @@ if has sweep; then
 fi
 
 if has ab; then
-  python tools/gen_ab.py > "$OUT/ab_geometries.txt"
+  python tools/gen_ab.py ${AB_LIST:-round2} > "$OUT/ab_geometries.txt"
   for lg in ${AB_SIZES:-28 26 25 24}; do
     reps=20; [ $lg -le 26 ] && reps=80; [ $lg -le 24 ] && reps=200; [ $lg -le 20 ] && reps=1000
     timeout 900 $PKG/b200va_tune --n $((1<<lg)) --reps $reps --warmup 3 --rounds 7 < "$OUT/ab_geometries.txt" > "$OUT/ab_2p$lg.jsonl" 2> "$OUT/ab_2p$lg.err"
