@@ -203,15 +203,15 @@ void default_tune(int variant, size_t n, b200va_tune_t* t)
             t->threads = 256;
             t->unroll = 1;
             return;
-        case B200VA_K2_TMA:
+        case B200VA_K2_TMA:               // TMA ring + cluster-launch-control scheduler (profiles/r01/i_ab_*)
             t->kind = B200VA_K2_TMA;
-            t->threads = 128;          // consumer threads (+32 producer)
+            t->threads = n >= (size_t{1} << 25) ? 512 : 128;   // consumer threads (+32 producer)
             t->ctas_per_sm = 1;
             t->ld_hint = LD_PLAIN;
             t->st_hint = ST_NA;
-            t->stages = 4;
+            t->stages = n >= (size_t{1} << 25) ? 8 : 3;
             t->tile_bytes = 8192;
-            t->store_mode = 0;
+            t->store_mode = 2;
             return;
         case B200VA_K1_VEC128:
             t->kind = B200VA_K1_VEC128;
