@@ -151,16 +151,17 @@ def cpu_quota() -> float:
 
 
 def best_thread_count(n: int = 1 << 26) -> tuple[int, dict[int, float]]:
-    """All the host threads the add can USE: tries the affinity count, the cgroup quota and
-    a few in between on a short sample and returns the fastest (threads, {threads: elem/s})."""
+    """All the host threads the add can USE: tries the affinity count, multiples of the cgroup
+    quota and a few fixed counts on a short sample (median of 3 passes each) and returns the
+    fastest (threads, {threads: elem/s})."""
     ncpu, quota = num_cpus(), cpu_quota()
     cands = {ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 8), min(ncpu, 16), min(ncpu, 32)}
     if quota > 0:
-        cands |= {max(1, min(ncpu, int(round(quota)))), max(1, min(ncpu, int(round(2 * quota))))}
+        cands |= {max(1, min(ncpu, int(round(k * quota)))) for k in (1, 1.5, 2, 3, 4)}
     rates = {}
     for t in sorted(cands):
-        secs = time_vadd_mt(n, t, 1, 2)
-        rates[t] = n / min(secs)
+        secs = sorted(time_vadd_mt(n, t, 1, 3))
+        rates[t] = n / secs[1]
     return max(rates, key=rates.get), rates
 
 

@@ -49,3 +49,22 @@ def test_replay_reference_shape_vs_sustained_loop():
     ev = r.run(busy, 120)
     assert ev[0][2] == 3 or ev[1][2] == 3                       # jumps straight to maxReplicas
     assert hr.would_scale_up(6.0) and not hr.would_scale_up(5.2)
+
+
+def test_recorded_gpu_run_replays_to_the_same_decisions():
+    """profiles/r01/g_hpa_trigger_replay.jsonl: NVML utilisation measured on a B200 while the
+    load generator ran at several duty cycles; the offline rule + HPA must agree with it."""
+    import json
+
+    path = os.path.join(ROOT, "profiles", "r01", "g_hpa_trigger_replay.jsonl")
+    if not os.path.exists(path):
+        pytest.skip("recorded run not present")
+    rows = [json.loads(l) for l in open(path)]
+    assert len(rows) >= 5
+    for r in rows:
+        want_up = r["nvml_util_mean"] > hr.HPA_TARGET * (1 + hr.HPA_TOLERANCE)
+        assert hr.would_scale_up(r["nvml_util_mean"]) == want_up == r["steady_state_would_scale_up"]
+        final_replicas = r["replay_events_t_metric_replicas"][-1][2]
+        assert (final_replicas > 1) == want_up
+        if isinstance(r["target_util"], (int, float)):
+            assert abs(r["nvml_util_mean"] - r["target_util"]) <= max(1.5, 0.1 * r["target_util"])   # controller accuracy
