@@ -286,7 +286,11 @@ def run_ours(args) -> None:
                                           f"{oracle.cpu_quota() or 'none'}), oracle/vadd_oracle.c (reference ships no source: "
                                           "port of its arithmetic)",
                                 "algorithmic_GBps": v * BYTES_PER_ELEM / 1e9}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
+
+
+def _emit(line: str) -> None:      # replaced in main() by the fd-switching version
+    print(line, flush=True)
 
 
 def main() -> None:
@@ -308,9 +312,22 @@ def main() -> None:
     if args.impl == "reference":
         run_reference(args)
         return
+    # stdout carries exactly ONE JSON line: while the run is in progress fd 1 points at stderr,
+    # so library banners (NCCL prints its version on stdout) cannot get in front of it
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(line: str) -> None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
     try:
         run_ours(args)
     finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         try:
             import torch.distributed as dist
 

@@ -30,8 +30,6 @@ def init(backend: str) -> bool:
     if ws <= 1:
         return False
     if not dist.is_initialized():
-        # rank 0's stdout carries exactly one JSON line: NCCL's banner/debug goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         dist.init_process_group(backend=backend, rank=rank, world_size=ws)

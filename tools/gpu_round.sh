@@ -140,7 +140,7 @@ if has ncu; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:vadd_ -s 3 -c 2 -f -o "$OUT/prof_auto" \
       python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1
   echo "ncu full exit=$?" | tee -a "$OUT/status.txt"
-  for k in k0 k1 k2; do
+  for k in ${NCU_KERNELS:-k0 k1 k2}; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:vadd_ -s 3 -c 1 -f -o "$OUT/prof_$k" \
         $PKG/vectorAdd --mode resident --n 2^28 --iters 3 --kernel $k --verify none >> "$OUT/ncu_full.log" 2>&1
   done
