@@ -56,7 +56,8 @@ extern "C" {
 #define B200VA_K0_SCALAR   1   /* reference-shape control: 1 elem/thread, 256-thread CTAs,
                                   (n+255)/256 CTAs  (CUDA sample launch geometry, a5)   */
 #define B200VA_K1_VEC128   2   /* 128-bit ld/st.global.v4.f32, unrolled, cache-hinted   */
-#define B200VA_K2_TMA      3   /* persistent CTAs, cp.async.bulk (TMA) smem ring        */
+#define B200VA_K2_TMA      3   /* cp.async.bulk (TMA) smem ring; tiles handed out by the
+                                  cluster-launch-control scheduler (store_mode 2)        */
 #define B200VA_K3_VEC256   4   /* 256-bit ld/st.global.v8.f32 (PTX 8.8, sm_100)         */
 
 /* Explicit geometry for A/B experiments (b200va_add_f32_tuned). Zero = default.      */

@@ -17,6 +17,9 @@
 //                        copies of an A tile and a B tile into a `stages`-deep smem ring
 //                        (mbarrier complete_tx); consumer warps add from smem and either
 //                        store from registers or write back in place and bulk-store.
+//   K2c vadd_tma_clc     the same ring with Blackwell's cluster-launch-control scheduler:
+//                        one CTA per tile in the grid, resident CTAs cancel and take over
+//                        the not-yet-started ones (dynamic balance, persistent ring).
 //
 // Ragged sizes / alignment: pointers need only 4-byte alignment.  `head` scalar
 // elements are peeled so the vector body is 16/32-byte aligned, the < VW tail is
