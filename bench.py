@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 METRIC = "fp32 elements/sec on 2^28-elem vectorAdd"
 UNIT = "elements/s"
 N_PER_GPU = 1 << 28
+STAGE_MODE = 0       # host-path pipeline used for e2e (0 slot streams, 2 lanes); see profiles/r01
 BYTES_PER_ELEM = 12  # 4 read A + 4 read B + 4 write C
 
 
@@ -219,12 +220,13 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         with va.Stager(local_rank, args.chunk_elems, args.depth) as stg:
+            mode = 1 if args.zero_copy else args.stage_mode
             for _ in range(2):
-                stg.add(ha, hb, hc, variant=variant, zero_copy=args.zero_copy)
+                stg.add(ha, hb, hc, variant=variant, mode=mode)
             sharding.barrier()
             ms_e2e = 0.0
             for _ in range(e2e_steps):
-                ms_e2e += stg.add(ha, hb, hc, variant=variant, zero_copy=args.zero_copy)
+                ms_e2e += stg.add(ha, hb, hc, variant=variant, mode=mode)
             sharding.barrier()
         ms_e2e = sharding.max_over_ranks(ms_e2e)
         # the step's result must be the right one
@@ -235,8 +237,9 @@ def run_ours(args) -> None:
         del c2
         e2e = {"value": ws * n * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n * ws,
                "d2h_bytes_per_step": 4 * n * ws, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-               "path": "b200va_stager_add_f32 " + ("zero-copy kernel over PCIe" if args.zero_copy else
-                                                   "copy-engine pipeline: H2D(A,B) -> add -> D2H(C) per chunk"),
+               "path": "b200va_stager_add_f32 " + {0: "copy-engine pipeline, one stream per slot: H2D(A,B) -> add -> D2H(C) per chunk",
+                                                   1: "zero-copy kernel over PCIe",
+                                                   2: "copy-engine pipeline, one stream per direction (lanes): H2D(A,B) | add | D2H(C)"}[mode],
                "host_memory": "pinned" + (", write-combined inputs" if args.wc_inputs else ""),
                "host_numa_nodes_rank0": host_nodes}
         del ha, hb, hc
@@ -305,6 +308,7 @@ def main() -> None:
     ap.add_argument("--chunk-elems", type=int, default=0)
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--zero-copy", action="store_true")
+    ap.add_argument("--stage-mode", type=int, choices=[0, 2], default=STAGE_MODE)
     ap.add_argument("--wc-inputs", action="store_true", help="write-combined pinned memory for the H2D sources")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

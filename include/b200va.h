@@ -155,7 +155,9 @@ int b200va_digest_f32(const float *d, size_t n, uint64_t *d_out, void *stream);
 typedef struct b200va_stager b200va_stager_t;
 /* mode 0: copy-engine pipeline through HBM staging buffers;
  * mode 1: zero-copy kernel reading/writing pinned host memory directly over PCIe
- *         (requires all three host buffers pinned/registered).                        */
+ *         (requires all three host buffers pinned/registered);
+ * mode 2: "lanes" pipeline: one stream per direction plus one for the adds, event edges
+ *         per slot, so the H2D queue never waits behind another chunk's kernel or D2H. */
 int b200va_stager_create(b200va_stager_t **out, int device, size_t chunk_elems, int depth);
 int b200va_stager_add_f32(b200va_stager_t *s, const float *hA, const float *hB, float *hC,
                           size_t n, int variant, int mode);

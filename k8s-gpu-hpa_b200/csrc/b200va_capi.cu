@@ -783,6 +783,9 @@ struct b200va_stager {
     cudaStream_t* slot = nullptr;
     cudaEvent_t* slot_done = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    // "lanes" pipeline (mode 2): one stream per direction + one for the kernel, events per slot
+    cudaStream_t lane_h2d = nullptr, lane_k = nullptr, lane_d2h = nullptr;
+    cudaEvent_t *ev_in = nullptr, *ev_sum = nullptr, *ev_out = nullptr;
     float last_ms = 0.f;
 };
 
@@ -883,6 +886,14 @@ int b200va_stager_destroy(b200va_stager_t* s)
             if (s->slot_done && s->slot_done[i]) cudaEventDestroy(s->slot_done[i]);
         }
     }
+    for (cudaStream_t st : {s->lane_h2d, s->lane_k, s->lane_d2h})
+        if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t* arr : {s->ev_in, s->ev_sum, s->ev_out}) {
+        if (!arr) continue;
+        for (int i = 0; i < s->depth; ++i)
+            if (arr[i]) cudaEventDestroy(arr[i]);
+        delete[] arr;
+    }
     if (s->main) cudaStreamDestroy(s->main);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
@@ -920,6 +931,17 @@ int b200va_stager_create(b200va_stager_t** out, int device, size_t chunk_elems, 
     }
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_start);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_stop);
+    s->ev_in = new (std::nothrow) cudaEvent_t[depth]();
+    s->ev_sum = new (std::nothrow) cudaEvent_t[depth]();
+    s->ev_out = new (std::nothrow) cudaEvent_t[depth]();
+    if (!s->ev_in || !s->ev_sum || !s->ev_out) { b200va_stager_destroy(s); return B200VA_ERR_NOMEM; }
+    for (cudaStream_t* st : {&s->lane_h2d, &s->lane_k, &s->lane_d2h})
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
+    for (int i = 0; i < depth && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_sum[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) { b200va_stager_destroy(s); return cuda_err(e); }
     *out = s;
     return B200VA_OK;
@@ -968,6 +990,34 @@ int b200va_stager_add_f32(b200va_stager_t* s, const float* hA, const float* hB, 
             CU_TRY(cudaEventRecord(s->slot_done[i], s->slot[i]));
             CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[i], 0));
         }
+    } else if (mode == 2) {
+        // lanes: every H2D copy queues on one stream, every add on a second, every D2H on a
+        // third; slot reuse and data flow are event edges.  The H2D queue -- the bottleneck
+        // direction -- never waits behind a kernel or a D2H of another chunk.
+        const size_t nchunks = (n + s->chunk - 1) / s->chunk;
+        for (cudaStream_t st : {s->lane_h2d, s->lane_k, s->lane_d2h}) CU_TRY(cudaStreamWaitEvent(st, s->ev_start, 0));
+        b200va_tune_t t;
+        for (size_t k = 0; k < nchunks; ++k) {
+            const int i = static_cast<int>(k % static_cast<size_t>(s->depth));
+            const size_t off = k * s->chunk;
+            const size_t m = (n - off < s->chunk) ? n - off : s->chunk;
+            float* dA = s->d_buf + static_cast<size_t>(i) * 3 * s->chunk;
+            float* dB = dA + s->chunk;
+            float* dC = dB + s->chunk;
+            if (k >= static_cast<size_t>(s->depth)) CU_TRY(cudaStreamWaitEvent(s->lane_h2d, s->ev_out[i], 0));  // slot drained
+            CU_TRY(cudaMemcpyAsync(dA, hA + off, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
+            CU_TRY(cudaMemcpyAsync(dB, hB + off, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
+            CU_TRY(cudaEventRecord(s->ev_in[i], s->lane_h2d));
+            CU_TRY(cudaStreamWaitEvent(s->lane_k, s->ev_in[i], 0));
+            default_tune(variant, m, &t);
+            RC_TRY(launch(dA, dB, dC, m, t, s->lane_k));
+            CU_TRY(cudaEventRecord(s->ev_sum[i], s->lane_k));
+            CU_TRY(cudaStreamWaitEvent(s->lane_d2h, s->ev_sum[i], 0));
+            CU_TRY(cudaMemcpyAsync(hC + off, dC, m * sizeof(float), cudaMemcpyDeviceToHost, s->lane_d2h));
+            CU_TRY(cudaEventRecord(s->ev_out[i], s->lane_d2h));
+        }
+        CU_TRY(cudaEventRecord(s->slot_done[0], s->lane_d2h));   // the D2H lane finishes last
+        CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[0], 0));
     } else {
         return B200VA_ERR_INVALID;
     }

@@ -196,11 +196,14 @@ class Stager:
         self._h = C.c_void_p()
         check(lib.b200va_stager_create(C.byref(self._h), device, chunk_elems, depth), "b200va_stager_create")
 
-    def add(self, a, b, out, *, variant=K_AUTO, zero_copy: bool = False) -> float:
-        """Synchronous; returns the device-timed milliseconds of the whole pipeline."""
+    def add(self, a, b, out, *, variant=K_AUTO, zero_copy: bool = False, mode: int | None = None) -> float:
+        """Synchronous; returns the device-timed milliseconds of the whole pipeline.
+        mode: 0 slot streams, 1 zero-copy kernel, 2 lanes (one stream per direction)."""
         n = a.size if isinstance(a, np.ndarray) else a.numel()
+        if mode is None:
+            mode = 1 if zero_copy else 0
         check(lib.b200va_stager_add_f32(self._h, _host_ptr(a, "a"), _host_ptr(b, "b"), _host_ptr(out, "out"), n,
-                                        _variant(variant), 1 if zero_copy else 0), "b200va_stager_add_f32")
+                                        _variant(variant), mode), "b200va_stager_add_f32")
         ms = C.c_float()
         check(lib.b200va_stager_last_ms(self._h, C.byref(ms)), "b200va_stager_last_ms")
         return ms.value

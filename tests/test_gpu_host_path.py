@@ -22,8 +22,8 @@ def test_add_host_pageable_arrays(n):
     assert oracle.first_mismatch(out, oracle.vadd(ha, hb)) == -1
 
 
-@pytest.mark.parametrize("zero_copy", [False, True])
-@pytest.mark.parametrize("chunk,depth", [(1 << 16, 2), (1 << 20, 3), (0, 0)])
+@pytest.mark.parametrize("zero_copy", [0, 1, 2])         # slot streams, zero-copy kernel, lanes
+@pytest.mark.parametrize("chunk,depth", [(1 << 16, 2), (1 << 20, 3), (1 << 18, 1), (0, 0)])
 def test_stager_pinned_pipeline(zero_copy, chunk, depth):
     n = 5_000_011
     ha = torch.from_numpy(oracle.fill_ctr(n, 0x0A, 1)).pin_memory()
@@ -33,7 +33,7 @@ def test_stager_pinned_pipeline(zero_copy, chunk, depth):
     with va.Stager(0, chunk, depth) as st:
         for m in (n, n - 3, 1 << 16, 7):
             hc.fill_(-1.0)
-            ms = st.add(ha[:m], hb[:m], hc[:m], zero_copy=zero_copy)
+            ms = st.add(ha[:m], hb[:m], hc[:m], mode=zero_copy)
             assert ms > 0
             assert oracle.first_mismatch(hc[:m].numpy(), want[:m]) == -1
             assert bool((hc[m:] == -1.0).all())

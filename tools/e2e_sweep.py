@@ -14,10 +14,10 @@ import torch  # noqa: E402
 from k8s_gpu_hpa_b200 import vector_add as va  # noqa: E402
 
 
-def run(n, ha, hb, hc, chunk, depth, zero_copy, steps=5):
+def run(n, ha, hb, hc, chunk, depth, mode, steps=5):
     with va.Stager(0, chunk, depth) as st:
-        st.add(ha, hb, hc, zero_copy=zero_copy)
-        ms = [st.add(ha, hb, hc, zero_copy=zero_copy) for _ in range(steps)]
+        st.add(ha, hb, hc, mode=int(mode))
+        ms = [st.add(ha, hb, hc, mode=int(mode)) for _ in range(steps)]
     ms.sort()
     return ms[len(ms) // 2], ms[0]
 
@@ -29,7 +29,7 @@ def main():
     b = torch.empty_like(a)
     va.fill_ctr(a, 0x0A)
     va.fill_ctr(b, 0x0B)
-    placements = [("b200va_host_alloc(auto numa)", None), ("numa node 0", "0"), ("numa node 1", "1"), ("torch pin_memory", "torch")]
+    placements = [("b200va_host_alloc(auto numa)", None)]
     for label, node in placements:
         if node == "torch":
             bufs = None
@@ -48,7 +48,7 @@ def main():
         ha.copy_(a); hb.copy_(b)
         torch.cuda.synchronize()
         grid = [(1 << 22, 3, False), (0, 0, True)] if label != "b200va_host_alloc(auto numa)" else \
-            [(c, d, False) for c in (1 << 20, 1 << 21, 1 << 22, 1 << 23, 1 << 24, 1 << 25) for d in (2, 3, 4, 6)] + [(0, 0, True)]
+            [(c, d, m) for m in (0, 2) for c in (1 << 20, 1 << 21, 1 << 22, 1 << 23, 1 << 24, 1 << 25) for d in (2, 3, 4, 6)] + [(0, 0, 1)]
         for chunk, depth, zc in grid:
             med, best = run(n, ha, hb, hc, chunk, depth, zc)
             c = torch.empty_like(a); c.copy_(hc)
