@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 METRIC = "fp32 elements/sec on 2^28-elem vectorAdd"
 UNIT = "elements/s"
 N_PER_GPU = 1 << 28
-STAGE_MODE = 0       # host-path pipeline used for e2e (0 slot streams, 2 lanes); see profiles/r01
+STAGE_MODE = 2       # host-path pipeline used for e2e (0 slot streams, 2 lanes: 42.25 vs 42.56 ms, profiles/r01/m_*)
 BYTES_PER_ELEM = 12  # 4 read A + 4 read B + 4 write C
 
 

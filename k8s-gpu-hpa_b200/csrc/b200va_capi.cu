@@ -1040,7 +1040,7 @@ int b200va_add_f32_host(const float* hA, const float* hB, float* hC, size_t n, i
     size_t chunk = size_t{1} << 23;
     if (n < chunk) chunk = n ? n : 1;
     RC_TRY(b200va_stager_create(&s, device, chunk, n > chunk ? 3 : 1));
-    const int rc = b200va_stager_add_f32(s, hA, hB, hC, n, variant, 0);
+    const int rc = b200va_stager_add_f32(s, hA, hB, hC, n, variant, 2);
     b200va_stager_destroy(s);
     return rc;
 }

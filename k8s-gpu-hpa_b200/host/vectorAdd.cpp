@@ -83,7 +83,7 @@ struct Options {
     double hpa_threshold = 5.0;
     bool cpu_baseline = false;
     int cpu_threads = 0;
-    int stage_mode = 0;
+    int stage_mode = 2;          // staged mode pipeline: 2 lanes (default), 0 slot streams, 1 zero-copy
     std::string json_path;
     bool any = false;
 };
@@ -166,6 +166,7 @@ Options parse(int argc, char** argv)
         else if (a == "--cpu-baseline") o.cpu_baseline = true;
         else if (a == "--cpu-threads") o.cpu_threads = std::atoi(need(i));
         else if (a == "--zero-copy") o.stage_mode = 1;
+        else if (a == "--slot-streams") o.stage_mode = 0;
         else if (a == "--json") o.json_path = need(i);
         else if (a == "--help" || a == "-h") {
             std::printf("usage: vectorAdd [--n N] [--iters K] [--gpus G] [--kernel auto|k0|k1|k2|k3]\n"
