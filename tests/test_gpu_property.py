@@ -1,0 +1,75 @@
+"""Property-based parity (hypothesis): random lengths, pointer offsets, kernel variants and
+bit patterns -- whatever the draw, the CUDA path returns the oracle's bits and writes
+nothing outside [0, n)."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import oracle
+from conftest import has_gpu
+
+pytestmark = pytest.mark.gpu
+if has_gpu():
+    import torch
+
+    from k8s_gpu_hpa_b200 import capi, vector_add as va
+
+SPECIAL = np.array([0x00000000, 0x80000000, 0x00000001, 0x807FFFFF, 0x00800000, 0x7F7FFFFF, 0xFF7FFFFF, 0x7F800000,
+                    0xFF800000, 0x7FC00000, 0x3F800000, 0xBF800000, 0x33800000, 0x4B000000], dtype=np.uint32)
+POOL = 1 << 18
+
+
+@pytest.fixture(scope="module")
+def pools():
+    rng = np.random.default_rng(1234)
+    ha = oracle.fill_ctr(POOL + 64, 0x0A, 11).view(np.uint32).copy()
+    hb = oracle.fill_ctr(POOL + 64, 0x0B, 11).view(np.uint32).copy()
+    # a quarter of the positions get arbitrary bit patterns, some get IEEE special values
+    for h in (ha, hb):
+        idx = rng.integers(0, h.size, h.size // 4)
+        h[idx] = rng.integers(0, 1 << 32, idx.size, dtype=np.uint64).astype(np.uint32)
+        idx = rng.integers(0, h.size, h.size // 16)
+        h[idx] = SPECIAL[rng.integers(0, SPECIAL.size, idx.size)]
+    ha, hb = ha.view(np.float32), hb.view(np.float32)
+    return ha, hb, torch.from_numpy(ha).cuda(), torch.from_numpy(hb).cuda()
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.one_of(st.integers(0, 70), st.integers(0, POOL)), oa=st.integers(0, 9), ob=st.integers(0, 9),
+       oc=st.integers(0, 9), variant=st.sampled_from(["auto", "k0", "k1", "k2", "k3"]), same=st.booleans())
+def test_random_lengths_offsets_variants(pools, n, oa, ob, oc, variant, same):
+    ha, hb, a, b = pools
+    if same:
+        ob = oc = oa            # equal misalignment: vector body with peeled head
+    out = torch.full((n + 32,), -3.0, dtype=torch.float32, device="cuda")
+    va.add(a[oa:oa + n], b[ob:ob + n], out[oc:oc + n], variant=variant)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    want = oracle.vadd(ha[oa:oa + n].copy(), hb[ob:ob + n].copy())
+    assert oracle.first_mismatch(got[oc:oc + n].copy(), want) == -1
+    assert (got[:oc] == -3.0).all() and (got[oc + n:] == -3.0).all()
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(1, POOL), threads=st.sampled_from([32, 64, 96, 128, 256, 320, 512, 1024]),
+       unroll=st.sampled_from([1, 2, 4, 8]), cps=st.sampled_from([0, 1, 3]), ld=st.integers(0, 5), stt=st.integers(0, 3),
+       wide=st.booleans())
+def test_random_vec_geometries(pools, n, threads, unroll, cps, ld, stt, wide):
+    ha, hb, a, b = pools
+    t = capi.Tune(kind=capi.K3_VEC256 if wide else capi.K1_VEC128, threads=threads, unroll=unroll, ctas_per_sm=cps,
+                  ld_hint=ld, st_hint=stt)
+    out = va.add(a[:n], b[:n], tune=t)
+    torch.cuda.synchronize()
+    assert oracle.first_mismatch(out.cpu().numpy(), oracle.vadd(ha[:n].copy(), hb[:n].copy())) == -1
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(1, POOL), threads=st.sampled_from([32, 64, 128, 256, 512]), stages=st.integers(2, 9),
+       tile_k=st.sampled_from([2048, 4096, 8192, 12288, 16384]), mode=st.integers(0, 2), hint=st.booleans())
+def test_random_tma_geometries(pools, n, threads, stages, tile_k, mode, hint):
+    ha, hb, a, b = pools
+    t = capi.Tune(kind=capi.K2_TMA, threads=threads, ctas_per_sm=1, ld_hint=3 if hint else 0, st_hint=1, stages=stages,
+                  tile_bytes=tile_k, store_mode=mode)
+    out = va.add(a[:n], b[:n], tune=t)
+    torch.cuda.synchronize()
+    assert oracle.first_mismatch(out.cpu().numpy(), oracle.vadd(ha[:n].copy(), hb[:n].copy())) == -1
