@@ -395,6 +395,17 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
     }
     vec_fn fn = pick_vec(vw, t.unroll, t.ld_hint, t.st_hint);
     if (!fn) return B200VA_ERR_VARIANT;
+    if (g.block > 512) {   // deep unrolls hold 2*UNROLL vectors in registers: the CTA size is then register-limited
+        thread_local vec_fn last_fn = nullptr;
+        thread_local unsigned last_max = 0;
+        if (fn != last_fn) {
+            cudaFuncAttributes fa;
+            CU_TRY(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(fn)));
+            last_fn = fn;
+            last_max = static_cast<unsigned>(fa.maxThreadsPerBlock);
+        }
+        if (g.block > last_max) return B200VA_ERR_VARIANT;
+    }
     return launch_kernel(fn, g.grid, g.block, 0, stream, dA, dB, dC, n, head, nvec, g.ntiles);
 }
 

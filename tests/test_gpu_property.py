@@ -58,7 +58,12 @@ def test_random_vec_geometries(pools, n, threads, unroll, cps, ld, stt, wide):
     ha, hb, a, b = pools
     t = capi.Tune(kind=capi.K3_VEC256 if wide else capi.K1_VEC128, threads=threads, unroll=unroll, ctas_per_sm=cps,
                   ld_hint=ld, st_hint=stt)
-    out = va.add(a[:n], b[:n], tune=t)
+    try:
+        out = va.add(a[:n], b[:n], tune=t)
+    except capi.B200VAError as e:
+        # the only legal refusal: a register-limited CTA size (1024 threads x 16 live 256-bit vectors)
+        assert e.code == capi.ERR_VARIANT and threads == 1024 and unroll == 8
+        return
     torch.cuda.synchronize()
     assert oracle.first_mismatch(out.cpu().numpy(), oracle.vadd(ha[:n].copy(), hb[:n].copy())) == -1
 
