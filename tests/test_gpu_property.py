@@ -75,6 +75,12 @@ def test_random_tma_geometries(pools, n, threads, stages, tile_k, mode, hint):
     ha, hb, a, b = pools
     t = capi.Tune(kind=capi.K2_TMA, threads=threads, ctas_per_sm=1, ld_hint=3 if hint else 0, st_hint=1, stages=stages,
                   tile_bytes=tile_k, store_mode=mode)
+    ring = stages * 2 * tile_k + (44 * stages + 16 if mode == 2 else 16 * stages)
+    if ring > 227 * 1024:           # does not fit the 227 KiB opt-in shared memory: must be refused, not launched
+        with pytest.raises(capi.B200VAError) as e:
+            va.add(a[:n], b[:n], tune=t)
+        assert e.value.code == capi.ERR_VARIANT
+        return
     out = va.add(a[:n], b[:n], tune=t)
     torch.cuda.synchronize()
     assert oracle.first_mismatch(out.cpu().numpy(), oracle.vadd(ha[:n].copy(), hb[:n].copy())) == -1
