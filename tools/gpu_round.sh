@@ -86,6 +86,9 @@ fi
 if has cli; then
   ( cd $PKG
     timeout 300 ./vectorAdd > "../$OUT/cli_default.log" 2>&1; echo "cli default exit=$?" | tee -a "../$OUT/status.txt"
+    # the reference's own shape (cuda-test-deployment.yaml:19), 20 iterations instead of 5000: wall time per process
+    T0=$(date +%s.%N); bash -c "for (( c=1; c<=20; c++ )); do ./vectorAdd; done" > /dev/null 2>&1; T1=$(date +%s.%N)
+    python -c "print('{\"bash_loop_iterations\": 20, \"wall_s\": %.3f, \"s_per_process\": %.4f}' % ($T1-$T0, ($T1-$T0)/20))" > "../$OUT/cli_bash_loop.json"
     timeout 600 ./vectorAdd --mode resident --n 2^28 --iters 100 --cpu-baseline --json "../$OUT/cli_2p28.json" > /dev/null 2>> "../$OUT/cli.err"
     timeout 600 ./vectorAdd --mode resident --n 2^24 --iters 5000 --nvml --duration 20 --json "../$OUT/cli_hpa_replay.json" > /dev/null 2>> "../$OUT/cli.err"
     timeout 600 ./vectorAdd --mode resident --n 2^24 --iters 5000 --graph 100 --json "../$OUT/cli_loop_graph.json" > /dev/null 2>> "../$OUT/cli.err"
