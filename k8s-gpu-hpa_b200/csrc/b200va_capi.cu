@@ -57,18 +57,22 @@ int dev_info(int device, const b200va_devinfo_t** out)
     if (device < 0 || device >= kMaxDevices) return B200VA_ERR_INVALID;
     DevCache& dc = g_dev[device];
     std::call_once(dc.once, [&] {
-        cudaDeviceProp p;
-        cudaError_t e = cudaGetDeviceProperties(&p, device);
+        // individual attributes, not cudaGetDeviceProperties: the latter queries everything
+        // and costs tens of milliseconds of every short-lived ./vectorAdd process
+        int major = 0, minor = 0, sms = 0, smem = 0, l2 = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device);
         if (e != cudaSuccess) { dc.rc = cuda_err(e); return; }
         dc.info.device = device;
-        dc.info.cc_major = p.major;
-        dc.info.cc_minor = p.minor;
-        dc.info.sm_count = p.multiProcessorCount;
-        dc.info.max_smem_optin = static_cast<int>(p.sharedMemPerBlockOptin);
-        dc.info.l2_bytes = p.l2CacheSize;
-        dc.info.global_mem_bytes = p.totalGlobalMem;
-        std::snprintf(dc.info.name, sizeof dc.info.name, "%s", p.name);
-        dc.rc = (p.major == 10) ? B200VA_OK : B200VA_ERR_NO_DEVICE;
+        dc.info.cc_major = major;
+        dc.info.cc_minor = minor;
+        dc.info.sm_count = sms;
+        dc.info.max_smem_optin = smem;
+        dc.info.l2_bytes = l2;
+        dc.rc = (major == 10) ? B200VA_OK : B200VA_ERR_NO_DEVICE;
     });
     if (out) *out = &dc.info;
     return dc.rc;
@@ -374,7 +378,13 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
         vw = (vw == 8) ? 4 : 0;
     }
     Geometry g;
-    if (vw == 0) {  // scalar control / mixed misalignment
+    if (vw == 0 && t.kind != B200VA_K0_SCALAR) {   // mixed misalignment: unrolled 4-byte kernel
+        constexpr int U = 8;
+        const size_t blocks = (n + 256 * U - 1) / (256 * U);
+        if (blocks > 0x7fffffffull) return B200VA_ERR_INVALID;
+        return launch_kernel(vadd_scalar_unrolled<U>, static_cast<unsigned>(blocks), 256u, 0, stream, dA, dB, dC, n);
+    }
+    if (vw == 0) {  // the scalar control
         b200va_tune_t k0{};
         k0.kind = B200VA_K0_SCALAR;
         RC_TRY(plan_geometry(k0, di, n, 0, &g));
@@ -502,7 +512,13 @@ int b200va_query(int device, b200va_devinfo_t* out)
     if (!out) return B200VA_ERR_INVALID;
     const b200va_devinfo_t* di = nullptr;
     const int rc = dev_info(device, &di);
-    if (di && (rc == B200VA_OK || rc == B200VA_ERR_NO_DEVICE) && di->sm_count > 0) *out = *di;
+    if (!di || di->sm_count <= 0) return rc;
+    *out = *di;
+    cudaDeviceProp p;                       // name and memory size: only this (cold) call pays for them
+    if (cudaGetDeviceProperties(&p, device) == cudaSuccess) {
+        out->global_mem_bytes = p.totalGlobalMem;
+        std::snprintf(out->name, sizeof out->name, "%s", p.name);
+    }
     return rc;
 }
 

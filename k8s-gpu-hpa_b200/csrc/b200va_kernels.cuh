@@ -39,6 +39,33 @@ __global__ void vadd_scalar(const float* A, const float* B, float* C, size_t n)
     if (i < n) C[i] = __fadd_rn(A[i], B[i]);
 }
 
+// Fallback when A, B and C are misaligned *differently* (no common 16-byte phase, so no
+// vector body exists): 4-byte accesses, but U independent coalesced loads per array per
+// thread in flight instead of the control's one.  Tile = blockDim.x * U elements.
+template <int U>
+__global__ void vadd_scalar_unrolled(const float* A, const float* B, float* C, size_t n)
+{
+    const size_t base = static_cast<size_t>(blockIdx.x) * blockDim.x * U + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    float a[U], b[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const size_t i = base + static_cast<size_t>(j) * blockDim.x;
+        a[j] = i < n ? A[i] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const size_t i = base + static_cast<size_t>(j) * blockDim.x;
+        b[j] = i < n ? B[i] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        const size_t i = base + static_cast<size_t>(j) * blockDim.x;
+        if (i < n) C[i] = __fadd_rn(a[j], b[j]);
+    }
+}
+
 // --------------------------------------------------------------------------- K1/K3
 template <int VW> struct vec_t;
 template <> struct vec_t<4> { using type = f32x4; };

@@ -307,8 +307,6 @@ int run_sample(const Options& o)
         });
     }
 
-    b200va_devinfo_t di;
-    va(b200va_query(0, &di), "find a B200-class CUDA device");
     float *d_A = nullptr, *d_B = nullptr, *d_C = nullptr;
     ck(cudaMalloc(&d_A, size ? size : 4), "allocate device vector A");
     ck(cudaMalloc(&d_B, size ? size : 4), "allocate device vector B");
