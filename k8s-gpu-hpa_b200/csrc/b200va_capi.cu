@@ -461,14 +461,30 @@ int launch_stream_typed(const void* dA, const void* dB, void* dC, size_t n, doub
     else if (m > (size_t{1} << 23)) { threads = 128; unroll = 2; }
     else if (m >= (size_t{1} << 21)) { threads = 256; unroll = 2; }
     else if (m >= (size_t{1} << 19)) { threads = 512; }
+    // development knob for profiles/: B200VA_STREAM_GEOMETRY="threads,unroll,skip_l1_stores"
+    static const struct Override { int threads = 0, unroll = 0, na = 0; } ov = [] {
+        Override o;
+        if (const char* e = std::getenv("B200VA_STREAM_GEOMETRY")) std::sscanf(e, "%d,%d,%d", &o.threads, &o.unroll, &o.na);
+        return o;
+    }();
+    if (ov.threads >= 32 && ov.threads <= 1024 && (ov.threads & 31) == 0 && (ov.unroll == 1 || ov.unroll == 2 || ov.unroll == 4)) {
+        threads = static_cast<unsigned>(ov.threads);
+        unroll = ov.unroll;
+        skip_l1_stores = ov.na != 0;
+    }
     const size_t tile_vecs = static_cast<size_t>(threads) * unroll;
     size_t grid = (nvec + tile_vecs - 1) / tile_vecs;
     if (grid > 0x7fffffffull) grid = 0x7fffffffull;
     if (grid == 0) grid = 1;
     const size_t ntiles = (nvec + tile_vecs - 1) / tile_vecs;
     using fn_t = void (*)(const void*, const void*, void*, size_t, size_t, size_t, size_t, S);
-    fn_t fn = skip_l1_stores ? (unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_NA> : stream_vec<DT, OP, 1, LD_PLAIN, ST_NA>)
-                             : (unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_PLAIN> : stream_vec<DT, OP, 1, LD_PLAIN, ST_PLAIN>);
+    fn_t fn = nullptr;
+    if (skip_l1_stores)
+        fn = unroll == 4 ? stream_vec<DT, OP, 4, LD_PLAIN, ST_NA> : unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_NA>
+                                                                                : stream_vec<DT, OP, 1, LD_PLAIN, ST_NA>;
+    else
+        fn = unroll == 4 ? stream_vec<DT, OP, 4, LD_PLAIN, ST_PLAIN> : unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_PLAIN>
+                                                                                   : stream_vec<DT, OP, 1, LD_PLAIN, ST_PLAIN>;
     return launch_kernel(fn, static_cast<unsigned>(grid), threads, 0, st, dA, dB, dC, n, head, nvec, ntiles, s);
 }
 

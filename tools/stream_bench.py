@@ -22,7 +22,10 @@ ARRAYS = {"copy": 2, "scale": 2, "add": 3, "triad": 3}
 def main():
     nbytes = 1 << 30
     reps, rounds = 20, 5
+    only = os.environ.get("STREAM_BENCH_DTYPES", "f32,f64,f16,bf16").split(",")
     for dt, tdt in TORCH.items():
+        if dt not in only:
+            continue
         n = nbytes // ES[dt]
         a = (torch.rand(n, device="cuda", dtype=torch.float32) * 2 - 1).to(tdt) if dt != "f64" else torch.rand(n, device="cuda", dtype=tdt)
         b = (torch.rand(n, device="cuda", dtype=torch.float32) * 2 - 1).to(tdt) if dt != "f64" else torch.rand(n, device="cuda", dtype=tdt)
@@ -52,7 +55,7 @@ def main():
             ms.sort()
             med = ms[len(ms) // 2]
             moved = ARRAYS[op] * nbytes
-            print(json.dumps({"dtype": dt, "op": op, "n": n, "bytes_per_launch": moved, "ms_median": med, "ms_best": ms[0],
+            print(json.dumps({"geometry": os.environ.get("B200VA_STREAM_GEOMETRY", "default"), "dtype": dt, "op": op, "n": n, "bytes_per_launch": moved, "ms_median": med, "ms_best": ms[0],
                               "GBps": moved / med / 1e6, "elements_per_s": n / (med * 1e-3), "first_mismatch": bad}), flush=True)
         del a, b, c
 
