@@ -457,8 +457,13 @@ int launch_stream_typed(const void* dA, const void* dB, void* dC, size_t n, doub
     unsigned threads = 128;
     int unroll = 1;
     bool skip_l1_stores = false;
-    if (m >= (size_t{1} << 25)) { threads = 512; skip_l1_stores = true; }
-    else if (m > (size_t{1} << 23)) { threads = 128; unroll = 2; }
+    if (m >= (size_t{1} << 25)) {
+        // three-array ops like the add: 512 x 1; two-array ops (copy, scale) want twice the bytes in
+        // flight per thread: 1024 x 2 is 7.04 TB/s vs 6.41 (profiles/r01/r_stream_geometry.jsonl)
+        threads = binary ? 512 : 1024;
+        unroll = binary ? 1 : 2;
+        skip_l1_stores = true;
+    } else if (m > (size_t{1} << 23)) { threads = 128; unroll = 2; }
     else if (m >= (size_t{1} << 21)) { threads = 256; unroll = 2; }
     else if (m >= (size_t{1} << 19)) { threads = 512; }
     // development knob for profiles/: B200VA_STREAM_GEOMETRY="threads,unroll,skip_l1_stores"
