@@ -214,7 +214,8 @@ def run_ours(args) -> None:
         # pinned host buffers from the C ABI (pages on the GPU's NUMA node), filled from the
         # device arrays outside the timed region
         pa, pb, pc = va.PinnedBuffer(n, args.wc_inputs), va.PinnedBuffer(n, args.wc_inputs), va.PinnedBuffer(n)
-        host_nodes = [p.numa_node for p in (pa, pb, pc)]
+        # [gpu's NUMA node, node of A, B, C] for every rank: the pinned buffers should sit next to their GPU
+        host_nodes = sharding.gather_ints([int(pkg.capi.lib.b200va_device_numa_node())] + [p.numa_node for p in (pa, pb, pc)])
         ha, hb, hc = (torch.from_numpy(p.array) for p in (pa, pb, pc))
         ha.copy_(a); hb.copy_(b)
         torch.cuda.synchronize()
@@ -241,7 +242,7 @@ def run_ours(args) -> None:
                                                    1: "zero-copy kernel over PCIe",
                                                    2: "copy-engine pipeline, one stream per direction (lanes): H2D(A,B) | add | D2H(C)"}[mode],
                "host_memory": "pinned" + (", write-combined inputs" if args.wc_inputs else ""),
-               "host_numa_nodes_rank0": host_nodes}
+               "numa_gpu_A_B_C_per_rank": host_nodes}
         del ha, hb, hc
         for p in (pa, pb, pc):
             p.free()

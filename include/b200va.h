@@ -176,6 +176,8 @@ int b200va_host_alloc_ex(void **out, size_t bytes, int write_combined);
 int b200va_host_free(void *p);
 /* NUMA node that holds the page at p, or -1 if it cannot be determined. */
 int b200va_host_node_of(const void *p);
+/* NUMA node the current CUDA device is attached to, or -1. */
+int b200va_device_numa_node(void);
 
 /* ---- generalised streaming element-wise core -------------------
  * The tuned 128-bit streaming skeleton of the vectorAdd kernel over other element types

@@ -82,6 +82,7 @@ _SIGS = {
     "b200va_host_alloc_ex": (_I, [C.POINTER(_P), _SZ, _I]),
     "b200va_host_free": (_I, [_P]),
     "b200va_host_node_of": (_I, [_P]),
+    "b200va_device_numa_node": (_I, []),
     "b200va_stream": (_I, [_I, _I, _P, _P, _P, _SZ, C.c_double, _P]),
     "b200va_shard_range": (_I, [_SZ, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
 }

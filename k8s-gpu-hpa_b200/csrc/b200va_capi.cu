@@ -906,6 +906,9 @@ int b200va_host_alloc_ex(void** out, size_t bytes, int write_combined)
 
 int b200va_host_alloc(void** out, size_t bytes) { return b200va_host_alloc_ex(out, bytes, 0); }
 
+// NUMA node the current CUDA device is attached to (sysfs), or -1.
+int b200va_device_numa_node(void) { return device_numa_node(); }
+
 // NUMA node holding the page at `p` (get_mempolicy(MPOL_F_NODE | MPOL_F_ADDR)), or -1.
 int b200va_host_node_of(const void* p)
 {

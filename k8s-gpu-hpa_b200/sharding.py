@@ -97,3 +97,16 @@ def combine_digests(local: tuple[int, int]) -> tuple[int, int]:
         s = (s + (v[0] | v[1] << 16 | v[2] << 32 | v[3] << 48)) & _MASK
         x ^= v[4] | v[5] << 16 | v[6] << 32 | v[7] << 48
     return s, x
+
+
+def gather_ints(values: list[int]) -> list[list[int]]:
+    """Every rank's small list of ints, on every rank (diagnostics only)."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        return [list(values)]
+    mine = torch.tensor(values, dtype=torch.int64, device=_reduce_device())
+    every = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(every, mine)
+    return [[int(v) for v in t.tolist()] for t in every]

@@ -35,6 +35,7 @@ def _worker(rank: int, world: int, port: int, n: int, out):
     local = oracle.bits_digest(oracle.vadd(a_, b_))
     sharding.barrier()
     glob = sharding.combine_digests(local)
+    assert sharding.gather_ints([rank, 7]) == [[r, 7] for r in range(world)]
     slowest = sharding.max_over_ranks(10.0 + rank)
     total = sharding.sum_over_ranks(float(e - b))
     out.put((rank, b, e, glob, slowest, total))
