@@ -64,6 +64,13 @@ if has sanitizer; then
   echo "synccheck k2 exit=$?" | tee -a "$OUT/status.txt"
 fi
 
+if has sanitizer2; then
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x -k "misalignment and (auto or k2)" > "$OUT/sanitizer2_parity.log" 2>&1
+  echo "memcheck pytest misalignment exit=$?" | tee -a "$OUT/status.txt"
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_stream.py -q -x -k "misaligned" > "$OUT/sanitizer2_stream.log" 2>&1
+  echo "memcheck pytest stream exit=$?" | tee -a "$OUT/status.txt"
+fi
+
 if has tests; then
   timeout 1500 python -m pytest tests -q -m gpu -x > "$OUT/pytest_gpu.log" 2>&1; echo "pytest gpu exit=$?" | tee -a "$OUT/status.txt"
   tail -5 "$OUT/pytest_gpu.log"
