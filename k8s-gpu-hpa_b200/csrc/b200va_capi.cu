@@ -1045,13 +1045,22 @@ int b200va_stager_add_f32(b200va_stager_t* s, const float* hA, const float* hB, 
         // lanes: every H2D copy queues on one stream, every add on a second, every D2H on a
         // third; slot reuse and data flow are event edges.  The H2D queue -- the bottleneck
         // direction -- never waits behind a kernel or a D2H of another chunk.
-        const size_t nchunks = (n + s->chunk - 1) / s->chunk;
         for (cudaStream_t st : {s->lane_h2d, s->lane_k, s->lane_d2h}) CU_TRY(cudaStreamWaitEvent(st, s->ev_start, 0));
         b200va_tune_t t;
-        for (size_t k = 0; k < nchunks; ++k) {
+        // Full-size chunks, then a tapered tail (1/2, 1/4, ... down to ~1 Mi elements): what is left
+        // after the last H2D byte has arrived is one small add and one small D2H, not a full chunk.
+        const size_t taper_min = size_t{1} << 20;
+        size_t off = 0;
+        for (size_t k = 0; off < n; ++k) {
+            const size_t left = n - off;
+            size_t m = s->chunk;
+            if (left <= s->chunk && s->depth > 1) {
+                m = left / 2;
+                m = (m + 63) & ~size_t{63};                      // chunk starts stay 256-byte aligned
+                if (m < taper_min || m >= left) m = left;
+            }
+            if (m > left) m = left;
             const int i = static_cast<int>(k % static_cast<size_t>(s->depth));
-            const size_t off = k * s->chunk;
-            const size_t m = (n - off < s->chunk) ? n - off : s->chunk;
             float* dA = s->d_buf + static_cast<size_t>(i) * 3 * s->chunk;
             float* dB = dA + s->chunk;
             float* dC = dB + s->chunk;
@@ -1066,6 +1075,7 @@ int b200va_stager_add_f32(b200va_stager_t* s, const float* hA, const float* hB, 
             CU_TRY(cudaStreamWaitEvent(s->lane_d2h, s->ev_sum[i], 0));
             CU_TRY(cudaMemcpyAsync(hC + off, dC, m * sizeof(float), cudaMemcpyDeviceToHost, s->lane_d2h));
             CU_TRY(cudaEventRecord(s->ev_out[i], s->lane_d2h));
+            off += m;
         }
         CU_TRY(cudaEventRecord(s->slot_done[0], s->lane_d2h));   // the D2H lane finishes last
         CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[0], 0));
