@@ -158,7 +158,8 @@ typedef struct b200va_stager b200va_stager_t;
  *         (requires all three host buffers pinned/registered);
  * mode 2: "lanes" pipeline: one stream per direction plus one for the adds, event edges
  *         per slot, so the H2D queue never waits behind another chunk's kernel or D2H. */
-/* chunk_elems = 0 -> 8 Mi elements (32 MiB per array per slot), depth = 0 -> 3 slots. */
+/* chunk_elems = 0 -> 32 Mi elements (128 MiB per array per slot), depth = 0 -> 3 slots.
+ * The lanes pipeline tapers the last chunk (1/2, 1/4, ... ~1 Mi) so the D2H tail is short. */
 int b200va_stager_create(b200va_stager_t **out, int device, size_t chunk_elems, int depth);
 int b200va_stager_add_f32(b200va_stager_t *s, const float *hA, const float *hB, float *hC,
                           size_t n, int variant, int mode);

@@ -960,7 +960,7 @@ int b200va_stager_create(b200va_stager_t** out, int device, size_t chunk_elems, 
 {
     if (!out) return B200VA_ERR_INVALID;
     *out = nullptr;
-    if (chunk_elems == 0) chunk_elems = size_t{1} << 23;   // 32 MiB per array per slot (e2e sweep: 8-16 Mi best)
+    if (chunk_elems == 0) chunk_elems = size_t{1} << 25;   // 128 MiB per array per slot (tapered tail: profiles/r01/u_*, v_*)
     if (depth == 0) depth = 3;
     if (depth < 1 || depth > 16) return B200VA_ERR_INVALID;
     chunk_elems = (chunk_elems + 63) & ~size_t{63};        // slots stay 256-B aligned
@@ -1098,7 +1098,7 @@ int b200va_stager_last_ms(b200va_stager_t* s, float* ms)
 int b200va_add_f32_host(const float* hA, const float* hB, float* hC, size_t n, int device, int variant)
 {
     b200va_stager_t* s = nullptr;
-    size_t chunk = size_t{1} << 23;
+    size_t chunk = size_t{1} << 25;
     if (n < chunk) chunk = n ? n : 1;
     RC_TRY(b200va_stager_create(&s, device, chunk, n > chunk ? 3 : 1));
     const int rc = b200va_stager_add_f32(s, hA, hB, hC, n, variant, 2);
