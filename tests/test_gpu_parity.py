@@ -276,6 +276,31 @@ def test_full_size_2p30_in_8_shards_checksum_of_checksums():
     assert (s, x) == oracle.ctr_vadd_digest(n)
 
 
+def test_beyond_32_bit_indexing_n_2p32_plus():
+    """n > 2^32 elements (48 GiB of operands): every index and byte offset must be 64-bit.
+    The sample's `int numElements` shape would wrap here; checked through the digest of the
+    whole result and the device recompute, plus an oracle window straddling element 2^32."""
+    n = (1 << 32) + 12_345
+    free, _ = torch.cuda.mem_get_info()
+    if free < 3 * 4 * n + (2 << 30):
+        pytest.skip("needs ~50 GiB of free device memory")
+    a = torch.empty(n, dtype=torch.float32, device="cuda")
+    b = torch.empty(n, dtype=torch.float32, device="cuda")
+    c = torch.empty(n, dtype=torch.float32, device="cuda")
+    va.fill_ctr(a, 0x0A)
+    va.fill_ctr(b, 0x0B)
+    want = oracle.ctr_vadd_digest(n)
+    lo, m = (1 << 32) - 4096, 12_000                       # window across the 2^32 boundary
+    win = oracle.vadd(oracle.fill_ctr(m, 0x0A, lo), oracle.fill_ctr(m, 0x0B, lo))
+    for variant in ("auto", "k2", "k0"):
+        c.zero_()
+        va.add(a, b, c, variant=variant)
+        assert va.digest(c) == want, variant
+        assert va.verify(a, b, c) == (0, -1), variant
+        assert_bits_equal(c[lo:lo + m], win, variant)
+        assert_bits_equal(c[n - 5000:], oracle.vadd(oracle.fill_ctr(5000, 0x0A, n - 5000), oracle.fill_ctr(5000, 0x0B, n - 5000)), variant)
+
+
 def test_launch_loop_matches_single_launch_with_and_without_graphs():
     n = 1 << 22
     a = torch.empty(n, dtype=torch.float32, device="cuda")
