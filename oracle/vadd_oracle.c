@@ -17,6 +17,9 @@
  *     a2  h_A[i] = rand()/(float)RAND_MAX; h_B[i] = rand()/(float)RAND_MAX  (no srand)
  *     a4  C[i] = A[i] + B[i]          IEEE-754 binary32, round-to-nearest-even
  *     a6  fabs(h_A[i] + h_B[i] - h_C[i]) > 1e-5  -> "Result verification failed"
+ * (Its launch shape -- N = 50000, 256 threads, (N+255)/256 blocks, guard i < N -- is
+ * corroborated by NVIDIA's int-typed derivatives shipped with this toolkit:
+ * /usr/local/cuda/extras/CUPTI/samples/cupti_nvtx/cupti_nvtx.cu:41-53,71,150-153.)
  * Because binary32 RNE addition has exactly one correct result for non-NaN operands,
  * the oracle is pinned by the IEEE-754 standard instead: oracle_softfloat_add_f32()
  * below is an integer-only implementation written from the standard, and
