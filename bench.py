@@ -155,7 +155,7 @@ def run_reference(args) -> None:
 
 
 # --------------------------------------------------------------------------- our arm
-def run_ours(args) -> None:
+def run_ours(args, emit=print) -> None:
     import torch
 
     import k8s_gpu_hpa_b200 as pkg
@@ -290,11 +290,29 @@ def run_ours(args) -> None:
                                           f"{oracle.cpu_quota() or 'none'}), oracle/vadd_oracle.c (reference ships no source: "
                                           "port of its arithmetic)",
                                 "algorithmic_GBps": v * BYTES_PER_ELEM / 1e9}
-    _emit(json.dumps(line))
+    emit(json.dumps(line))
 
 
-def _emit(line: str) -> None:      # replaced in main() by the fd-switching version
-    print(line, flush=True)
+class SingleLineStdout:
+    """stdout carries exactly ONE JSON line: while the run is in progress fd 1 points at stderr,
+    so library banners (NCCL prints its version on stdout) cannot get in front of it."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self.emit
+
+    def emit(self, line: str) -> None:
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
 
 
 def main() -> None:
@@ -317,22 +335,10 @@ def main() -> None:
     if args.impl == "reference":
         run_reference(args)
         return
-    # stdout carries exactly ONE JSON line: while the run is in progress fd 1 points at stderr,
-    # so library banners (NCCL prints its version on stdout) cannot get in front of it
-    sys.stdout.flush()
-    saved_stdout = os.dup(1)
-    os.dup2(2, 1)
-    global _emit
-    def _emit(line: str) -> None:
-        sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
-        print(line, flush=True)
-        os.dup2(2, 1)
     try:
-        run_ours(args)
+        with SingleLineStdout() as emit:
+            run_ours(args, emit)
     finally:
-        sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
         try:
             import torch.distributed as dist
 
