@@ -416,40 +416,52 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
         }
     }
 
-    auto run_block = [&]() {   // one block of o.iters passes, event-timed
+    double last_ms_per_pass = 0.0;
+    auto run_block = [&](int count) {   // one block of `count` passes, event-timed
+        const double before = r.gpu_ms;
         if (staged) {
-            for (int i = 0; i < o.iters && ok; ++i) {
+            for (int i = 0; i < count && ok; ++i) {
                 VA(b200va_stager_add_f32(stager, hA, hB, hC, m, o.variant, o.stage_mode), "staged add");
                 float ms = 0; if (ok) b200va_stager_last_ms(stager, &ms);
                 r.gpu_ms += ms;
             }
         } else {
             CK(cudaEventRecord(e0, st), "record event");
-            VA(b200va_loop_run(loop, o.iters, st), "launch vectorAdd kernel");
+            VA(b200va_loop_run(loop, count, st), "launch vectorAdd kernel");
             CK(cudaEventRecord(e1, st), "record event");
             CK(cudaEventSynchronize(e1), "synchronize");
             float ms = 0; if (ok) CK(cudaEventElapsedTime(&ms, e0, e1), "read event");
             r.gpu_ms += ms;
         }
-        r.launches += o.iters;
+        r.launches += count;
+        if (count > 0) last_ms_per_pass = (r.gpu_ms - before) / count;
     };
 
     bar.wait();
     const auto t0 = clk::now();
     if (o.duration <= 0) {
-        if (ok) run_block();
+        if (ok) run_block(o.iters);
     } else {
         const double period = o.period_ms * 1e-3;
         double next_sample = 0.0;
         while (ok && secs_since(t0) < o.duration) {
             const auto p0 = clk::now();
             if (o.target_util > 0) {     // busy for target% of the period, then idle
+                // busy budget of this period, spent in blocks of at most --iters passes; the block is
+                // shrunk to what still fits so that small targets (a few %) are not overshot
                 const double budget = period * o.target_util / 100.0;
-                do { run_block(); } while (ok && secs_since(p0) < budget);
+                do {
+                    int count = o.iters;
+                    if (last_ms_per_pass > 0) {
+                        const double fit = (budget - secs_since(p0)) * 1e3 / last_ms_per_pass;
+                        count = static_cast<int>(std::max(1.0, std::min(static_cast<double>(o.iters), fit)));
+                    }
+                    run_block(count);
+                } while (ok && secs_since(p0) < budget - 0.5e-3 * last_ms_per_pass);
                 const double rest = period - secs_since(p0);
                 if (rest > 0) std::this_thread::sleep_for(std::chrono::duration<double>(rest));
             } else {
-                run_block();
+                run_block(o.iters);
             }
             if (nvml && secs_since(t0) >= next_sample) {
                 r.util_samples.push_back(nvml->gpu_util(static_cast<size_t>(rank)));
