@@ -59,6 +59,9 @@ extern "C" {
 #define B200VA_K2_TMA      3   /* cp.async.bulk (TMA) smem ring; tiles handed out by the
                                   cluster-launch-control scheduler (store_mode 2)        */
 #define B200VA_K3_VEC256   4   /* 256-bit ld/st.global.v8.f32 (PTX 8.8, sm_100)         */
+#define B200VA_K4_SCALAR_MLP 5 /* 32-bit accesses, `unroll` (4|8|16) independent loads per array
+                                  per thread in flight: the mixed-misalignment path, also
+                                  selectable through b200va_add_f32_tuned for A/B runs   */
 
 /* Explicit geometry for A/B experiments (b200va_add_f32_tuned). Zero = default.      */
 typedef struct b200va_tune {

@@ -21,7 +21,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200va.h")
 OK = 0
 ERR_INVALID, ERR_ALIGN, ERR_OVERLAP, ERR_VARIANT, ERR_NO_DEVICE, ERR_VERIFY, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 ERR_CUDA_BASE = -1000
-K_AUTO, K0_SCALAR, K1_VEC128, K2_TMA, K3_VEC256 = 0, 1, 2, 3, 4
+K_AUTO, K0_SCALAR, K1_VEC128, K2_TMA, K3_VEC256, K4_SCALAR_MLP = 0, 1, 2, 3, 4, 5
 OPS = {"copy": 0, "scale": 1, "add": 2, "triad": 3}
 DTYPES = {"f32": 0, "f64": 1, "f16": 2, "bf16": 3}
 VARIANTS = {"auto": K_AUTO, "k0": K0_SCALAR, "k1": K1_VEC128, "k2": K2_TMA, "k3": K3_VEC256}

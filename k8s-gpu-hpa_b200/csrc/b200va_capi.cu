@@ -364,7 +364,7 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
     int vw = 0;
     if (t.kind == B200VA_K3_VEC256) vw = 8;
     else if (t.kind == B200VA_K1_VEC128 || t.kind == B200VA_K2_TMA) vw = 4;
-    else if (t.kind != B200VA_K0_SCALAR) return B200VA_ERR_VARIANT;
+    else if (t.kind != B200VA_K0_SCALAR && t.kind != B200VA_K4_SCALAR_MLP) return B200VA_ERR_VARIANT;
 
     // vector body needs A, B, C equally misaligned w.r.t. the vector width
     size_t head = 0;
@@ -378,11 +378,19 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
         vw = (vw == 8) ? 4 : 0;
     }
     Geometry g;
-    if (vw == 0 && t.kind != B200VA_K0_SCALAR) {   // mixed misalignment: unrolled 4-byte kernel
-        constexpr int U = 8;
-        const size_t blocks = (n + 256 * U - 1) / (256 * U);
+    if (t.kind == B200VA_K4_SCALAR_MLP || (vw == 0 && t.kind != B200VA_K0_SCALAR)) {
+        // 4-byte kernel with U loads per array per thread in flight: explicit A/B variant, and the
+        // path taken when A, B, C share no 16-byte phase (no vector body exists)
+        const bool explicit_geo = t.kind == B200VA_K4_SCALAR_MLP;
+        const unsigned threads = explicit_geo ? static_cast<unsigned>(t.threads) : 256u;
+        const int U = explicit_geo ? t.unroll : 8;
+        if (threads < 32 || threads > 1024 || (threads & 31u)) return B200VA_ERR_VARIANT;
+        if (U != 4 && U != 8 && U != 16) return B200VA_ERR_VARIANT;
+        const size_t per_cta = static_cast<size_t>(threads) * static_cast<size_t>(U);
+        const size_t blocks = (n + per_cta - 1) / per_cta;
         if (blocks > 0x7fffffffull) return B200VA_ERR_INVALID;
-        return launch_kernel(vadd_scalar_unrolled<U>, static_cast<unsigned>(blocks), 256u, 0, stream, dA, dB, dC, n);
+        auto fn = U == 4 ? vadd_scalar_unrolled<4> : U == 8 ? vadd_scalar_unrolled<8> : vadd_scalar_unrolled<16>;
+        return launch_kernel(fn, static_cast<unsigned>(blocks), threads, 0, stream, dA, dB, dC, n);
     }
     if (vw == 0) {  // the scalar control
         b200va_tune_t k0{};
@@ -581,6 +589,10 @@ int b200va_add_f32_tuned(const float* dA, const float* dB, float* dC, size_t n,
     b200va_tune_t d;
     default_tune(t.kind, n, &d);
     if (t.kind == B200VA_K_AUTO) t = d;
+    if (t.kind == B200VA_K4_SCALAR_MLP) {
+        if (t.threads == 0) t.threads = 256;
+        if (t.unroll == 0) t.unroll = 8;
+    }
     if (t.threads == 0) t.threads = d.threads;
     if (t.unroll == 0) t.unroll = d.unroll ? d.unroll : 1;
     if (t.stages == 0) t.stages = d.stages;

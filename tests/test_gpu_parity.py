@@ -176,6 +176,9 @@ def test_tuned_geometries_are_all_bit_exact():
         for threads in (32, 128, 512):
             geos.append(capi.Tune(kind=capi.K2_TMA, threads=threads, ld_hint=0, st_hint=1, stages=stages, tile_bytes=tile,
                                   store_mode=2))
+    for threads in (32, 256, 1024):                                  # 4-byte accesses, U loads per array in flight
+        for unroll in (4, 8, 16):
+            geos.append(capi.Tune(kind=capi.K4_SCALAR_MLP, threads=threads, unroll=unroll))
     for t in geos:
         out = torch.full((n,), -1.0, dtype=torch.float32, device="cuda")
         va.add(a, b, out, tune=t)

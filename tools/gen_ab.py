@@ -13,6 +13,15 @@ if which == "round1":
     for threads, cps, stages, tile, mode in ((128, 1, 4, 8192, 0), (128, 2, 2, 8192, 0), (128, 1, 8, 4096, 0), (256, 1, 12, 4096, 1), (256, 1, 6, 16384, 1), (256, 1, 4, 8192, 0)):
         for ld in (0, 3):
             print(K2, threads, 0, cps, ld, 1, stages, tile, mode)
+elif which == "width":
+    # access width vs loads in flight: 4-byte x {4,8,16}, 16-byte x {1,2,4}, 32-byte x {1,2}
+    for threads in (128, 256, 512, 1024):
+        for u in (4, 8, 16):
+            print(5, threads, u, 0, 0, 0, 0, 0, 0)
+        for u in (1, 2, 4):
+            print(K1, threads, u, 0, 0, 1, 0, 0, 0)
+        for u in (1, 2):
+            print(K3, threads, u, 0, 0, 1, 0, 0, 0)
 elif which == "clc":
     print(K1, 512, 1, 0, 0, 1, 0, 0, 0)
     print(K3, 768, 2, 0, 0, 1, 0, 0, 0)

@@ -3,7 +3,7 @@
 import json
 import sys
 
-KIND = {1: "k0_scalar", 2: "k1_vec128", 3: "k2_tma", 4: "k3_vec256"}
+KIND = {1: "k0_scalar", 2: "k1_vec128", 3: "k2_tma", 4: "k3_vec256", 5: "k4_scalar_mlp"}
 
 
 def main():
@@ -22,7 +22,7 @@ def main():
     for r in bad[:20]:
         print("BAD", r)
     ok = [r for r in rows if r not in bad]
-    for kind in (1, 2, 4, 3):
+    for kind in (1, 2, 4, 3, 5):
         sel = sorted((r for r in ok if r["kind"] == kind), key=lambda r: r["ms_median"])
         print(f"\n## {KIND[kind]}: {len(sel)} geometries")
         print("threads unroll cps ld st stages tile mode | ms_med ms_best ms_mean | GB/s(med) GB/s(mean)")
