@@ -345,7 +345,25 @@ int launch_kernel(void (*fn)(KArgs...), unsigned grid, unsigned block, size_t sm
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cuda_err(cudaLaunchKernelEx(&cfg, fn, static_cast<KArgs>(args)...));
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, fn, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) cudaGetLastError();   // a refused launch must not stay latched for the next caller
+    return cuda_err(e);
+}
+
+// Largest CTA the kernel can be launched with (register-limited for the deep unrolls).
+template <class Fn>
+int check_block_size(Fn fn, unsigned block)
+{
+    thread_local const void* last_fn = nullptr;
+    thread_local unsigned last_max = 0;
+    const void* key = reinterpret_cast<const void*>(fn);
+    if (key != last_fn) {
+        cudaFuncAttributes fa;
+        CU_TRY(cudaFuncGetAttributes(&fa, key));
+        last_fn = key;
+        last_max = static_cast<unsigned>(fa.maxThreadsPerBlock);
+    }
+    return block > last_max ? B200VA_ERR_VARIANT : B200VA_OK;
 }
 
 int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t t, cudaStream_t stream)
@@ -390,6 +408,7 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
         const size_t blocks = (n + per_cta - 1) / per_cta;
         if (blocks > 0x7fffffffull) return B200VA_ERR_INVALID;
         auto fn = U == 4 ? vadd_scalar_unrolled<4> : U == 8 ? vadd_scalar_unrolled<8> : vadd_scalar_unrolled<16>;
+        if (threads > 256) RC_TRY(check_block_size(fn, threads));
         return launch_kernel(fn, static_cast<unsigned>(blocks), threads, 0, stream, dA, dB, dC, n);
     }
     if (vw == 0) {  // the scalar control
@@ -413,17 +432,7 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
     }
     vec_fn fn = pick_vec(vw, t.unroll, t.ld_hint, t.st_hint);
     if (!fn) return B200VA_ERR_VARIANT;
-    if (g.block > 512) {   // deep unrolls hold 2*UNROLL vectors in registers: the CTA size is then register-limited
-        thread_local vec_fn last_fn = nullptr;
-        thread_local unsigned last_max = 0;
-        if (fn != last_fn) {
-            cudaFuncAttributes fa;
-            CU_TRY(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(fn)));
-            last_fn = fn;
-            last_max = static_cast<unsigned>(fa.maxThreadsPerBlock);
-        }
-        if (g.block > last_max) return B200VA_ERR_VARIANT;
-    }
+    if (g.block > 512) RC_TRY(check_block_size(fn, g.block));   // deep unrolls: the CTA size is register-limited
     return launch_kernel(fn, g.grid, g.block, 0, stream, dA, dB, dC, n, head, nvec, g.ntiles);
 }
 

@@ -181,6 +181,14 @@ def test_tuned_geometries_are_all_bit_exact():
             geos.append(capi.Tune(kind=capi.K4_SCALAR_MLP, threads=threads, unroll=unroll))
     for t in geos:
         out = torch.full((n,), -1.0, dtype=torch.float32, device="cuda")
+        if t.kind == capi.K4_SCALAR_MLP and t.threads == 1024 and t.unroll == 16:
+            with pytest.raises(pkg.B200VAError) as e:        # 1024 threads x 32 live loads: register-limited, refused
+                va.add(a, b, out, tune=t)
+            assert e.value.code == capi.ERR_VARIANT
+            va.add(a, b, out)                                  # and the refusal leaves no latched CUDA error behind
+            torch.cuda.synchronize()
+            assert_bits_equal(out, want, "after refused launch")
+            continue
         va.add(a, b, out, tune=t)
         torch.cuda.synchronize()
         assert_bits_equal(out, want, str(t.as_dict()))
