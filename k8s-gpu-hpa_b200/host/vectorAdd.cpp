@@ -17,6 +17,7 @@
 //   --gpus G         shard [0,N) evenly over G GPUs      --kernel auto|k0|k1|k2|k3
 //   --mode sample|resident|staged                        --gen rand|ctr
 //   --graph B        capture B launches per CUDA graph   --verify full|none
+//   --seed S         ctr generator seeds: A = S, B = S+1 (default 0x0A)
 //   --duration S     repeat the K-launch block for S seconds of wall clock
 //   --target-util P  duty-cycle the blocks so the GPU is busy ~P % of each period
 //   --period-ms M    duty-cycle period (default 100)     --nvml  sample NVML utilisation
@@ -83,6 +84,7 @@ struct Options {
     double hpa_threshold = 5.0;
     bool cpu_baseline = false;
     int cpu_threads = 0;
+    uint64_t seed = 0x0A;        // ctr generator: A uses seed, B uses seed + 1 (defaults 0x0A / 0x0B)
     int stage_mode = 2;          // staged mode pipeline: 2 lanes (default), 0 slot streams, 1 zero-copy
     std::string json_path;
     bool any = false;
@@ -157,6 +159,7 @@ Options parse(int argc, char** argv)
         else if (a == "--mode") { o.mode = need(i); o.mode_set = true; }
         else if (a == "--gen") { o.gen = need(i); o.gen_set = true; }
         else if (a == "--graph") o.graph = std::atoi(need(i));
+        else if (a == "--seed") o.seed = std::strtoull(need(i), nullptr, 0);
         else if (a == "--verify") o.verify = std::strcmp(need(i), "none") != 0;
         else if (a == "--duration") o.duration = std::atof(need(i));
         else if (a == "--target-util") o.target_util = std::atof(need(i));
@@ -170,7 +173,7 @@ Options parse(int argc, char** argv)
         else if (a == "--json") o.json_path = need(i);
         else if (a == "--help" || a == "-h") {
             std::printf("usage: vectorAdd [--n N] [--iters K] [--gpus G] [--kernel auto|k0|k1|k2|k3]\n"
-                        "                 [--mode sample|resident|staged] [--gen rand|ctr] [--graph B]\n"
+                        "                 [--mode sample|resident|staged] [--gen rand|ctr] [--seed S] [--graph B]\n"
                         "                 [--verify full|none] [--duration S] [--target-util P] [--period-ms M]\n"
                         "                 [--nvml] [--hpa-threshold T] [--cpu-baseline] [--cpu-threads T]\n"
                         "                 [--zero-copy] [--json PATH]\n"
@@ -302,8 +305,8 @@ int run_sample(const Options& o)
         va(b200va_host_fill_rand_f32(h_A, h_B, n), "initialize host vectors");
     } else {
         parallel_spans(n, host_cpus(), [&](size_t lo, size_t hi) {
-            b200va_host_fill_ctr_f32(h_A + lo, hi - lo, 0x0A, lo);
-            b200va_host_fill_ctr_f32(h_B + lo, hi - lo, 0x0B, lo);
+            b200va_host_fill_ctr_f32(h_A + lo, hi - lo, o.seed, lo);
+            b200va_host_fill_ctr_f32(h_B + lo, hi - lo, o.seed + 1, lo);
         });
     }
 
@@ -399,16 +402,16 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
             VA(b200va_host_alloc(reinterpret_cast<void**>(&hB), m * 4), "allocate pinned B");
             VA(b200va_host_alloc(reinterpret_cast<void**>(&hC), m * 4), "allocate pinned C");
             if (ok) parallel_spans(m, std::max(1, host_cpus() / o.gpus), [&](size_t lo, size_t hi) {
-                b200va_host_fill_ctr_f32(hA + lo, hi - lo, 0x0A, b + lo);
-                b200va_host_fill_ctr_f32(hB + lo, hi - lo, 0x0B, b + lo);
+                b200va_host_fill_ctr_f32(hA + lo, hi - lo, o.seed, b + lo);
+                b200va_host_fill_ctr_f32(hB + lo, hi - lo, o.seed + 1, b + lo);
             });
             VA(b200va_stager_create(&stager, rank, 0, 0), "create stager");
         } else {
             CK(cudaMalloc(&dA, m ? m * 4 : 4), "allocate device vector A");
             CK(cudaMalloc(&dB, m ? m * 4 : 4), "allocate device vector B");
             CK(cudaMalloc(&dC, m ? m * 4 : 4), "allocate device vector C");
-            VA(b200va_fill_ctr_f32(dA, m, 0x0A, b, st), "generate A");   // global index => sharding invisible
-            VA(b200va_fill_ctr_f32(dB, m, 0x0B, b, st), "generate B");
+            VA(b200va_fill_ctr_f32(dA, m, o.seed, b, st), "generate A");   // global index => sharding invisible
+            VA(b200va_fill_ctr_f32(dB, m, o.seed + 1, b, st), "generate B");
             // warm-up
             VA(b200va_loop_create(&loop, dA, dB, dC, m, o.variant, o.graph), "capture launch loop");
             VA(b200va_loop_run(loop, std::max(3, o.graph), st), "warm up");

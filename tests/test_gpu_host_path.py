@@ -78,6 +78,20 @@ def test_cli_resident_mode_reports_oracle_digest():
     assert r["launches_per_gpu"] == 20 and r["elements_per_s"] > 1e9
 
 
+def test_cli_seed_changes_the_data_not_the_verdict():
+    n = 1 << 20
+    digests = set()
+    for seed in ("0x0A", "77"):
+        p = va.run_cli("--mode", "resident", "--n", str(n), "--iters", "3", "--seed", seed)
+        assert p.returncode == 0, p.stderr
+        r = json.loads(p.stdout.strip().splitlines()[-1])
+        assert r["mismatches"] == 0
+        digests.add(r["digest_sum"])
+        if seed == "0x0A":
+            assert int(r["digest_sum"], 16) == oracle.ctr_vadd_digest(n)[0]
+    assert len(digests) == 2
+
+
 def test_cli_staged_mode_and_duty_cycle():
     p = va.run_cli("--mode", "staged", "--n", str((1 << 23) + 1), "--iters", "2")
     assert p.returncode == 0, p.stderr
