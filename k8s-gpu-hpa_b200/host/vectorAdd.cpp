@@ -24,6 +24,7 @@
 //   --hpa-threshold T  utilisation the HPA compares with (default 5, cuda-test-hpa.yaml:21)
 //   --cpu-baseline   also time a host-threads C[i]=A[i]+B[i] loop (reported, never used)
 //   --json PATH      write the result line to PATH as well as stdout
+//   --metrics-file P rewrite P every 0.5 s with `dcgm_gpu_utilization{...} <NVML util>` (Prometheus text)
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <sched.h>
@@ -87,6 +88,7 @@ struct Options {
     uint64_t seed = 0x0A;        // ctr generator: A uses seed, B uses seed + 1 (defaults 0x0A / 0x0B)
     int stage_mode = 2;          // staged mode pipeline: 2 lanes (default), 0 slot streams, 1 zero-copy
     std::string json_path;
+    std::string metrics_file;    // Prometheus text snapshot of the NVML utilisation (GPU 0), rewritten every 0.5 s
     bool any = false;
 };
 
@@ -171,12 +173,13 @@ Options parse(int argc, char** argv)
         else if (a == "--zero-copy") o.stage_mode = 1;
         else if (a == "--slot-streams") o.stage_mode = 0;
         else if (a == "--json") o.json_path = need(i);
+        else if (a == "--metrics-file") { o.metrics_file = need(i); o.nvml = true; }
         else if (a == "--help" || a == "-h") {
             std::printf("usage: vectorAdd [--n N] [--iters K] [--gpus G] [--kernel auto|k0|k1|k2|k3]\n"
                         "                 [--mode sample|resident|staged] [--gen rand|ctr] [--seed S] [--graph B]\n"
                         "                 [--verify full|none] [--duration S] [--target-util P] [--period-ms M]\n"
                         "                 [--nvml] [--hpa-threshold T] [--cpu-baseline] [--cpu-threads T]\n"
-                        "                 [--zero-copy] [--json PATH]\n"
+                        "                 [--zero-copy] [--json PATH] [--metrics-file PATH]\n"
                         "no arguments: the reference image's behaviour (50000 elements, one add, verify).\n");
             std::exit(0);
         } else {
@@ -258,10 +261,12 @@ struct Nvml {
     using byid_t = int (*)(const char*, void**);
     struct Util { unsigned gpu, memory; };
     using util_t = int (*)(void*, Util*);
+    using uuid_t = int (*)(void*, char*, unsigned);
     void* lib = nullptr;
     shut_t shut = nullptr;
     util_t util = nullptr;
     std::vector<void*> dev;
+    std::vector<std::string> uuid;
     bool open(const std::vector<int>& cuda_devs)
     {
         lib = dlopen("libnvidia-ml.so.1", RTLD_NOW);
@@ -276,8 +281,27 @@ struct Nvml {
             void* h = nullptr;
             if (cudaDeviceGetPCIBusId(bus, sizeof bus, d) != cudaSuccess || byid(bus, &h) != 0) return false;
             dev.push_back(h);
+            char id[96] = "unknown";
+            if (auto get_uuid = reinterpret_cast<uuid_t>(dlsym(lib, "nvmlDeviceGetUUID"))) get_uuid(h, id, sizeof id);
+            uuid.emplace_back(id);
         }
         return true;
+    }
+    // One sample in the Prometheus text format under the metric name the reference's rule reads
+    // (cuda-test-prometheusrule.yaml:13), e.g. for node-exporter's textfile collector.  Written
+    // atomically (tmp + rename).  The pod label is what the rule joins on.
+    void write_metrics(const std::string& path, size_t i, int util_pct) const
+    {
+        const char* pod = std::getenv("HOSTNAME");
+        const std::string tmp = path + ".tmp";
+        if (FILE* f = std::fopen(tmp.c_str(), "w")) {
+            std::fprintf(f, "# HELP dcgm_gpu_utilization GPU utilization (in %%), NVML utilization.gpu as sampled by vectorAdd.\n"
+                            "# TYPE dcgm_gpu_utilization gauge\n"
+                            "dcgm_gpu_utilization{gpu=\"%zu\",uuid=\"%s\",pod=\"%s\",namespace=\"default\"} %d\n",
+                         i, i < uuid.size() ? uuid[i].c_str() : "unknown", pod ? pod : "", util_pct);
+            std::fclose(f);
+            std::rename(tmp.c_str(), path.c_str());
+        }
     }
     int gpu_util(size_t i) const
     {
@@ -468,6 +492,7 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
             }
             if (nvml && secs_since(t0) >= next_sample) {
                 r.util_samples.push_back(nvml->gpu_util(static_cast<size_t>(rank)));
+                if (!o.metrics_file.empty() && rank == 0) nvml->write_metrics(o.metrics_file, 0, r.util_samples.back());
                 next_sample += 0.5;
             }
         }

@@ -96,10 +96,18 @@ def test_cli_staged_mode_and_duty_cycle():
     p = va.run_cli("--mode", "staged", "--n", str((1 << 23) + 1), "--iters", "2")
     assert p.returncode == 0, p.stderr
     assert json.loads(p.stdout.strip().splitlines()[-1])["mismatches"] == 0
-    p = va.run_cli("--n", "2^22", "--iters", "50", "--duration", "1.0", "--target-util", "30", "--nvml")
-    assert p.returncode == 0, p.stderr
-    r = json.loads(p.stdout.strip().splitlines()[-1])
-    assert r["mismatches"] == 0 and 0.0 < r["gpu_busy_frac"] < 0.9
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        prom = d + "/gpu.prom"
+        p = va.run_cli("--n", "2^22", "--iters", "50", "--duration", "1.5", "--target-util", "30", "--metrics-file", prom)
+        assert p.returncode == 0, p.stderr
+        r = json.loads(p.stdout.strip().splitlines()[-1])
+        assert r["mismatches"] == 0 and 0.2 < r["gpu_busy_frac"] < 0.4
+        text = open(prom).read()                       # the series the reference's recording rule reads
+        assert "# TYPE dcgm_gpu_utilization gauge" in text
+        sample = [l for l in text.splitlines() if l.startswith("dcgm_gpu_utilization{")][0]
+        assert 'gpu="0"' in sample and "uuid=\"GPU-" in sample and 0 <= int(sample.rsplit(" ", 1)[1]) <= 100
 
 
 @pytest.mark.parametrize("gpus", [2, 4, 8])
