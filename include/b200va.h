@@ -160,7 +160,10 @@ typedef struct b200va_stager b200va_stager_t;
  * mode 1: zero-copy kernel reading/writing pinned host memory directly over PCIe
  *         (requires all three host buffers pinned/registered);
  * mode 2: "lanes" pipeline: one stream per direction plus one for the adds, event edges
- *         per slot, so the H2D queue never waits behind another chunk's kernel or D2H. */
+ *         per slot, so the H2D queue never waits behind another chunk's kernel or D2H;
+ * mode 3: pageable host arrays (plain malloc): host threads copy chunks through pinned
+ *         bounce buffers around the lanes pipeline.  b200va_add_f32_host picks 2 or 3
+ *         by asking the runtime whether the arrays are pinned. */
 /* chunk_elems = 0 -> 32 Mi elements (128 MiB per array per slot), depth = 0 -> 3 slots.
  * The lanes pipeline tapers the last chunk (1/2, 1/4, ... ~1 Mi) so the D2H tail is short. */
 int b200va_stager_create(b200va_stager_t **out, int device, size_t chunk_elems, int depth);

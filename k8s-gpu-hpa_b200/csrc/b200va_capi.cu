@@ -15,6 +15,10 @@
 
 #include <atomic>
 #include <cctype>
+#include <condition_variable>
+#include <functional>
+#include <thread>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -843,6 +847,71 @@ int b200va_shard_range(size_t n, int world, int rank, size_t* begin, size_t* end
 }
 
 // ------------------------------------------------------------------ host-buffer path
+// Fork-join pool for the pageable path: T persistent workers, each copies one slice.
+class CopyPool {
+public:
+    explicit CopyPool(int threads) : n_(threads < 1 ? 1 : threads)
+    {
+        for (int i = 1; i < n_; ++i) th_.emplace_back([this, i] { worker(i); });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int size() const { return n_; }
+    // dst[0..bytes) = src[0..bytes), split in 64-byte-aligned slices over the pool (caller = slice 0)
+    void copy(void* dst, const void* src, size_t bytes)
+    {
+        if (bytes < (size_t{1} << 20) || n_ == 1) { std::memcpy(dst, src, bytes); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            dst_ = static_cast<unsigned char*>(dst); src_ = static_cast<const unsigned char*>(src); bytes_ = bytes;
+            pending_ = n_ - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        slice(0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    void slice(int i)
+    {
+        size_t per = (bytes_ + static_cast<size_t>(n_) - 1) / static_cast<size_t>(n_);
+        per = (per + 63) & ~size_t{63};
+        const size_t lo = std::min(bytes_, per * static_cast<size_t>(i)), hi = std::min(bytes_, lo + per);
+        if (hi > lo) std::memcpy(dst_ + lo, src_ + lo, hi - lo);
+    }
+    void worker(int i)
+    {
+        unsigned long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            slice(i);
+            std::lock_guard<std::mutex> lk(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    unsigned long gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+    unsigned char* dst_ = nullptr;
+    const unsigned char* src_ = nullptr;
+    size_t bytes_ = 0;
+};
+
 struct b200va_stager {
     int device = 0;
     size_t chunk = 0;
@@ -855,6 +924,10 @@ struct b200va_stager {
     // "lanes" pipeline (mode 2): one stream per direction + one for the kernel, events per slot
     cudaStream_t lane_h2d = nullptr, lane_k = nullptr, lane_d2h = nullptr;
     cudaEvent_t *ev_in = nullptr, *ev_sum = nullptr, *ev_out = nullptr;
+    // pageable path (mode 3): pinned bounce chunks (depth * 3 * bounce_chunk floats) + copy threads, made on first use
+    float* bounce = nullptr;
+    size_t bounce_chunk = 0;
+    CopyPool* pool = nullptr;
     float last_ms = 0.f;
 };
 
@@ -970,6 +1043,8 @@ int b200va_stager_destroy(b200va_stager_t* s)
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
     if (s->d_buf) cudaFree(s->d_buf);
+    if (s->bounce) cudaFreeHost(s->bounce);
+    delete s->pool;
     delete[] s->slot;
     delete[] s->slot_done;
     delete s;
@@ -1100,6 +1175,65 @@ int b200va_stager_add_f32(b200va_stager_t* s, const float* hA, const float* hB, 
         }
         CU_TRY(cudaEventRecord(s->slot_done[0], s->lane_d2h));   // the D2H lane finishes last
         CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[0], 0));
+    } else if (mode == 3) {
+        // Pageable host arrays (plain malloc, what one ./vectorAdd process has): a cudaMemcpy from
+        // pageable memory is staged by the driver on one thread at ~10 GB/s.  Here a pool of host
+        // threads copies chunk k+1 into pinned bounce buffers and chunk k-2 out of them while the
+        // copy engines and the add work on the chunks in between (lanes as in mode 2).
+        const size_t bc = std::min(s->chunk, size_t{1} << 23);          // 32 MiB bounce chunks
+        if (!s->pool) {
+            unsigned hw = std::thread::hardware_concurrency();
+            cpu_set_t set;
+            if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) hw = static_cast<unsigned>(CPU_COUNT(&set));
+            s->pool = new (std::nothrow) CopyPool(static_cast<int>(std::max(1u, std::min(8u, hw))));
+            if (!s->pool) return B200VA_ERR_NOMEM;
+        }
+        if (!s->bounce || s->bounce_chunk != bc) {
+            if (s->bounce) { cudaFreeHost(s->bounce); s->bounce = nullptr; }
+            void* p = nullptr;
+            RC_TRY(b200va_host_alloc(&p, static_cast<size_t>(s->depth) * 3 * bc * sizeof(float)));
+            s->bounce = static_cast<float*>(p);
+            s->bounce_chunk = bc;
+        }
+        for (cudaStream_t st : {s->lane_h2d, s->lane_k, s->lane_d2h}) CU_TRY(cudaStreamWaitEvent(st, s->ev_start, 0));
+        const size_t nchunks = (n + bc - 1) / bc;
+        const size_t depth = static_cast<size_t>(s->depth);
+        b200va_tune_t t;
+        auto span = [&](size_t k, size_t* off, size_t* m) { *off = k * bc; *m = std::min(bc, n - *off); };
+        for (size_t k = 0; k < nchunks + depth - 1 || k < nchunks; ++k) {
+            if (k < nchunks) {
+                size_t off, m;
+                span(k, &off, &m);
+                const size_t i = k % depth;
+                float* pA = s->bounce + i * 3 * bc;
+                float* dA = s->d_buf + i * 3 * s->chunk;
+                // slot i was drained (copied out) at iteration k-1 below, or never used
+                s->pool->copy(pA, hA + off, m * sizeof(float));
+                s->pool->copy(pA + bc, hB + off, m * sizeof(float));
+                CU_TRY(cudaMemcpyAsync(dA, pA, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
+                CU_TRY(cudaMemcpyAsync(dA + s->chunk, pA + bc, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
+                CU_TRY(cudaEventRecord(s->ev_in[i], s->lane_h2d));
+                CU_TRY(cudaStreamWaitEvent(s->lane_k, s->ev_in[i], 0));
+                default_tune(variant, m, &t);
+                RC_TRY(launch(dA, dA + s->chunk, dA + 2 * s->chunk, m, t, s->lane_k));
+                CU_TRY(cudaEventRecord(s->ev_sum[i], s->lane_k));
+                CU_TRY(cudaStreamWaitEvent(s->lane_d2h, s->ev_sum[i], 0));
+                CU_TRY(cudaMemcpyAsync(pA + 2 * bc, dA + 2 * s->chunk, m * sizeof(float), cudaMemcpyDeviceToHost, s->lane_d2h));
+                CU_TRY(cudaEventRecord(s->ev_out[i], s->lane_d2h));
+            }
+            if (k + 1 >= depth) {                                       // retire chunk j = k - (depth - 1)
+                const size_t j = k + 1 - depth;
+                if (j < nchunks) {
+                    size_t off, m;
+                    span(j, &off, &m);
+                    const size_t i = j % depth;
+                    CU_TRY(cudaEventSynchronize(s->ev_out[i]));
+                    s->pool->copy(hC + off, s->bounce + i * 3 * bc + 2 * bc, m * sizeof(float));
+                }
+            }
+        }
+        CU_TRY(cudaEventRecord(s->slot_done[0], s->lane_d2h));
+        CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[0], 0));
     } else {
         return B200VA_ERR_INVALID;
     }
@@ -1121,8 +1255,16 @@ int b200va_add_f32_host(const float* hA, const float* hB, float* hC, size_t n, i
     b200va_stager_t* s = nullptr;
     size_t chunk = size_t{1} << 25;
     if (n < chunk) chunk = n ? n : 1;
+    // pinned/registered arrays go straight to the copy engines; pageable ones through the bounce pool
+    bool pageable = false;
+    for (const void* p : {static_cast<const void*>(hA), static_cast<const void*>(hB), static_cast<const void*>(hC)}) {
+        cudaPointerAttributes at{};
+        if (n && (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type == cudaMemoryTypeUnregistered)) pageable = true;
+    }
+    cudaGetLastError();
+    if (pageable && chunk > (size_t{1} << 23)) chunk = size_t{1} << 23;
     RC_TRY(b200va_stager_create(&s, device, chunk, n > chunk ? 3 : 1));
-    const int rc = b200va_stager_add_f32(s, hA, hB, hC, n, variant, 2);
+    const int rc = b200va_stager_add_f32(s, hA, hB, hC, n, variant, pageable ? 3 : 2);
     b200va_stager_destroy(s);
     return rc;
 }

@@ -15,14 +15,14 @@ if has_gpu():
     from k8s_gpu_hpa_b200 import capi, vector_add as va
 
 
-@pytest.mark.parametrize("n", [0, 1, 5, 50000, (1 << 22) + 3, 3 * (1 << 22) + 17])
+@pytest.mark.parametrize("n", [0, 1, 5, 50000, (1 << 22) + 3, 3 * (1 << 22) + 17, 5 * (1 << 23) + 1234567])
 def test_add_host_pageable_arrays(n):
     ha, hb = oracle.fill_ctr(n, 0x0A, 3), oracle.fill_ctr(n, 0x0B, 3)
     out = va.add_host(ha, hb)
     assert oracle.first_mismatch(out, oracle.vadd(ha, hb)) == -1
 
 
-@pytest.mark.parametrize("zero_copy", [0, 1, 2])         # slot streams, zero-copy kernel, lanes
+@pytest.mark.parametrize("zero_copy", [0, 1, 2, 3])      # slot streams, zero-copy kernel, lanes, pageable bounce
 @pytest.mark.parametrize("chunk,depth", [(1 << 16, 2), (1 << 20, 3), (1 << 18, 1), (0, 0)])
 def test_stager_pinned_pipeline(zero_copy, chunk, depth):
     n = 5_000_011
@@ -37,6 +37,19 @@ def test_stager_pinned_pipeline(zero_copy, chunk, depth):
             assert ms > 0
             assert oracle.first_mismatch(hc[:m].numpy(), want[:m]) == -1
             assert bool((hc[m:] == -1.0).all())
+
+
+def test_stager_pageable_mode_on_plain_numpy_arrays():
+    n = 30_000_001
+    ha, hb = oracle.fill_ctr(n, 0x0A, 9), oracle.fill_ctr(n, 0x0B, 9)
+    want = oracle.vadd(ha, hb)
+    for chunk, depth in ((1 << 20, 1), (1 << 21, 2), (1 << 22, 3), (0, 0)):
+        with va.Stager(0, chunk, depth) as st:
+            for m in (n, n - 5, 123):
+                hc = np.full(n, -1.0, np.float32)
+                st.add(ha[:m], hb[:m], hc[:m], mode=3)
+                assert oracle.first_mismatch(hc[:m].copy(), want[:m].copy()) == -1
+                assert (hc[m:] == -1.0).all()
 
 
 def test_cli_zero_arguments_is_the_reference_process():

@@ -24,6 +24,13 @@ for _ in range(3):
     dt = time.perf_counter() - t0
     print(json.dumps({"case": "b200va_add_f32_host, pageable arrays, one-shot (alloc+pipeline+free)", "ms": dt * 1e3,
                       "elements_per_s": n / dt}), flush=True)
+with va.Stager(0, 1 << 23, 3) as st:
+    for _ in range(3):
+        ms = st.add(a, b, c, mode=3)
+        print(json.dumps({"case": "stager mode 3 (pageable bounce), persistent stager", "ms": ms, "elements_per_s": n / (ms * 1e-3)}), flush=True)
+    for mode in (2, 0):
+        ms = st.add(a, b, c, mode=mode)
+        print(json.dumps({"case": f"stager mode {mode} fed pageable arrays (driver-staged cudaMemcpyAsync)", "ms": ms}), flush=True)
 bufs = [va.PinnedBuffer(n) for _ in range(3)]
 for p, src in zip(bufs[:2], (a, b)):
     p.array[:] = src
