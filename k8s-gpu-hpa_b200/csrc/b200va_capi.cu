@@ -1262,7 +1262,8 @@ int b200va_add_f32_host(const float* hA, const float* hB, float* hC, size_t n, i
         if (n && (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type == cudaMemoryTypeUnregistered)) pageable = true;
     }
     cudaGetLastError();
-    if (pageable && chunk > (size_t{1} << 23)) chunk = size_t{1} << 23;
+    // one-shot: pinning the bounce ring costs ~0.35 ms/MiB, so keep it small (9 x 8 MiB)
+    if (pageable && chunk > (size_t{1} << 21)) chunk = size_t{1} << 21;
     RC_TRY(b200va_stager_create(&s, device, chunk, n > chunk ? 3 : 1));
     const int rc = b200va_stager_add_f32(s, hA, hB, hC, n, variant, pageable ? 3 : 2);
     b200va_stager_destroy(s);

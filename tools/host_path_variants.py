@@ -24,6 +24,11 @@ for _ in range(3):
     dt = time.perf_counter() - t0
     print(json.dumps({"case": "b200va_add_f32_host, pageable arrays, one-shot (alloc+pipeline+free)", "ms": dt * 1e3,
                       "elements_per_s": n / dt}), flush=True)
+for ch in (1 << 20, 1 << 21, 1 << 22):
+    with va.Stager(0, ch, 3) as st:
+        st.add(a, b, c, mode=3)
+        ms = st.add(a, b, c, mode=3)
+        print(json.dumps({"case": f"stager mode 3, chunk {ch}, steady", "ms": ms}), flush=True)
 with va.Stager(0, 1 << 23, 3) as st:
     for _ in range(3):
         ms = st.add(a, b, c, mode=3)
