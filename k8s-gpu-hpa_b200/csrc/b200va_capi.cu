@@ -1182,10 +1182,21 @@ int b200va_stager_add_f32(b200va_stager_t* s, const float* hA, const float* hB, 
         // copy engines and the add work on the chunks in between (lanes as in mode 2).
         const size_t bc = std::min(s->chunk, size_t{1} << 23);          // 32 MiB bounce chunks
         if (!s->pool) {
+            // copy threads: the CPUs this process may use (affinity mask, cgroup v2 bandwidth quota), at most 16;
+            // B200VA_COPY_THREADS overrides
             unsigned hw = std::thread::hardware_concurrency();
             cpu_set_t set;
             if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) hw = static_cast<unsigned>(CPU_COUNT(&set));
-            s->pool = new (std::nothrow) CopyPool(static_cast<int>(std::max(1u, std::min(8u, hw))));
+            if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+                char q[64];
+                double period = 0;
+                if (std::fscanf(f, "%63s %lf", q, &period) == 2 && std::strcmp(q, "max") != 0 && period > 0)
+                    hw = std::min(hw, static_cast<unsigned>(std::max(1.0, std::atof(q) / period)));
+                std::fclose(f);
+            }
+            unsigned want = std::max(1u, std::min(16u, hw));
+            if (const char* e = std::getenv("B200VA_COPY_THREADS")) want = static_cast<unsigned>(std::max(1, std::atoi(e)));
+            s->pool = new (std::nothrow) CopyPool(static_cast<int>(want));
             if (!s->pool) return B200VA_ERR_NOMEM;
         }
         if (!s->bounce || s->bounce_chunk != bc) {
