@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 METRIC = "fp32 elements/sec on 2^28-elem vectorAdd"
 UNIT = "elements/s"
 N_PER_GPU = 1 << 28
+CLOCK_PERIOD_MS = 2.0
 STAGE_MODE = 2       # host-path pipeline used for e2e (0 slot streams, 2 lanes: 42.25 vs 42.56 ms, profiles/r01/m_*)
 BYTES_PER_ELEM = 12  # 4 read A + 4 read B + 4 write C
 
@@ -44,7 +45,8 @@ class ClockSampler:
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
                0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, cuda_index: int):
+    def __init__(self, cuda_index: int, period_s: float = 0.002):
+        self.period_s = period_s
         self.samples: list[int] = []
         self.reason_bits = 0
         self.max_mhz = None
@@ -77,7 +79,7 @@ class ClockSampler:
                     self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period_s)
 
     def __enter__(self):
         if self._h is not None:
@@ -189,7 +191,7 @@ def run_ours(args, emit=print) -> None:
     torch.cuda.synchronize()
     sharding.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_period_ms * 1e-3)
     torch.cuda.synchronize()
     with sampler:
         ev0.record(stream)
@@ -329,6 +331,7 @@ def main() -> None:
     ap.add_argument("--zero-copy", action="store_true")
     ap.add_argument("--stage-mode", type=int, choices=[0, 2], default=STAGE_MODE)
     ap.add_argument("--wc-inputs", action="store_true", help="write-combined pinned memory for the H2D sources")
+    ap.add_argument("--clock-period-ms", type=float, default=CLOCK_PERIOD_MS, help="NVML clock sampling period during the timed region")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
