@@ -24,6 +24,8 @@
  *     no hidden allocation; the caller owns every buffer.
  *   - The current CUDA device of the calling thread is used (cudaSetDevice first);
  *     the library is re-entrant and keeps only immutable per-device attribute caches.
+ *     Entry points that take a `device` argument (stager, b200va_add_f32_host, b200va_query)
+ *     restore the caller's current device before returning, on every path.
  *   - Element type is IEEE-754 binary32; the add is add.rn.f32 without FTZ, so results
  *     are bit-identical to a scalar C loop on the same inputs (NaN payloads excepted:
  *     PTX returns the canonical NaN 0x7fffffff).
@@ -38,7 +40,7 @@
 extern "C" {
 #endif
 
-#define B200VA_ABI_VERSION 1
+#define B200VA_ABI_VERSION 2   /* 2: b200va_tune_t grew early_loads/scheduler; *_ex, stager modes 4/AUTO */
 
 /* ---- status codes ------------------------------------------------------------- */
 #define B200VA_OK               0
@@ -50,6 +52,10 @@ extern "C" {
 #define B200VA_ERR_VERIFY      (-6)   /* result verification failed (a6)                  */
 #define B200VA_ERR_NOMEM       (-7)   /* host allocation failed                           */
 #define B200VA_ERR_CUDA_BASE   (-1000) /* code = -(1000 + cudaError_t)                    */
+/* Which combinations a library carries: libb200va.so ships the production set (what
+ * B200VA_K_AUTO and the named variants resolve to, plus a few neighbours); the full
+ * A/B matrix of b200va_tune_t lives in libb200va_tune.so (same ABI, development only).
+ * A combination the loaded library does not carry returns B200VA_ERR_VARIANT. */
 
 /* ---- kernel variants (argument `variant`) ---------------------------------------- */
 #define B200VA_K_AUTO      0   /* the tuned production choice for this n                */
@@ -75,6 +81,13 @@ typedef struct b200va_tune {
     int tile_bytes;   /* TMA: bytes per array per stage (multiple of 2048)              */
     int store_mode;   /* TMA: 0 = st.global from registers, 1 = bulk store from smem,
                          2 = register stores + cluster-launch-control tile scheduler    */
+    int early_loads;  /* vec: 1 = issue the first tile's loads before the programmatic
+                         dependency on the previous launch resolves (only stores wait).
+                         Requires that the previous launch on the stream does not write A
+                         or B; forced to 0 when C aliases A or B.  See b200va_add_f32_ex. */
+    int scheduler;    /* vec: 0 = hardware block scheduler (one CTA per tile, or the static
+                         persistent split of ctas_per_sm), 1 = cluster launch control:
+                         resident CTAs cancel and take over not-yet-started ones (K1c)   */
 } b200va_tune_t;
 
 typedef struct b200va_devinfo {
@@ -108,13 +121,25 @@ int b200va_add_f32(const float *dA, const float *dB, float *dC, size_t n,
                    int variant, void *stream);
 int b200va_add_f32_tuned(const float *dA, const float *dB, float *dC, size_t n,
                          const b200va_tune_t *tune, void *stream);
+/* Same as b200va_add_f32 with launch-ordering hints (`flags`, OR of B200VA_F_*).
+ * B200VA_F_INPUTS_STABLE: the caller promises that the launch immediately preceding this
+ * one on `stream` does not write A or B (e.g. it is another add into a different or the
+ * same C).  The kernel then issues its loads while that launch is still draining and only
+ * its stores wait for it (programmatic dependent launch), which removes most of the
+ * ~2 us bubble between back-to-back launches.  Results and stream order of C are
+ * unchanged; the flag is ignored when C aliases A or B. */
+#define B200VA_F_INPUTS_STABLE 1u
+int b200va_add_f32_ex(const float *dA, const float *dB, float *dC, size_t n,
+                      int variant, unsigned flags, void *stream);
 
 /* ---- a1: the launch loop, in-process -----------------------------------------------
  * Replaces the 5000-process bash loop (cuda-test-deployment.yaml:19): `iters`
  * back-to-back launches on `stream`; graph_batch > 1 captures that many launches into
  * one CUDA graph and replays it (launch-bound sizes).  Asynchronous, except that the
  * graph form (graph_batch > 1) drains the stream before returning; any capturable or
- * legacy stream is accepted (the capture happens on a private stream). */
+ * legacy stream is accepted (the capture happens on a private stream).
+ * Launches 2..iters of a loop know their predecessor (the same add, which writes only C),
+ * so unless C aliases A or B they run with early loads (see B200VA_F_INPUTS_STABLE). */
 int b200va_add_f32_loop(const float *dA, const float *dB, float *dC, size_t n,
                         int variant, int iters, int graph_batch, void *stream);
 /* Persistent form for a long-running load generator: the graph of `graph_batch` launches
@@ -163,14 +188,36 @@ typedef struct b200va_stager b200va_stager_t;
  *         per slot, so the H2D queue never waits behind another chunk's kernel or D2H;
  * mode 3: pageable host arrays (plain malloc): host threads copy chunks through pinned
  *         bounce buffers around the lanes pipeline.  b200va_add_f32_host picks 2 or 3
- *         by asking the runtime whether the arrays are pinned. */
+ *         by asking the runtime whether the arrays are pinned.
+ * mode 4: register-once: pageable arrays are page-locked in place (cudaHostRegister) the
+ *         first time the stager sees them and the registration is cached by address range,
+ *         so a long-lived loop over the same malloc'd arrays -- the reference process's
+ *         shape -- runs the lanes pipeline at the pinned rate from the second call on.
+ *         The first call pays the pinning (~0.3 ms/MiB).  Registered arrays must stay
+ *         allocated until b200va_stager_release_host / b200va_stager_destroy.  Falls back
+ *         to mode 3 if the registration is refused (RLIMIT_MEMLOCK, exotic mappings).
+ * mode -1 (B200VA_STAGE_AUTO): mode 2 for pinned arrays, mode 4 for pageable arrays of at
+ *         least 8 MiB in total, mode 3 below that. */
+#define B200VA_STAGE_AUTO      (-1)
+#define B200VA_STAGE_SLOTS       0
+#define B200VA_STAGE_ZEROCOPY    1
+#define B200VA_STAGE_LANES       2
+#define B200VA_STAGE_BOUNCE      3
+#define B200VA_STAGE_REGISTER    4
 /* chunk_elems = 0 -> 32 Mi elements (128 MiB per array per slot), depth = 0 -> 3 slots.
  * The lanes pipeline tapers the last chunk (1/2, 1/4, ... ~1 Mi) so the D2H tail is short. */
 int b200va_stager_create(b200va_stager_t **out, int device, size_t chunk_elems, int depth);
+/* Synchronous.  On an error in the middle of the pipeline every stream of the stager is
+ * drained before the call returns, so no copy is still touching the caller's arrays. */
 int b200va_stager_add_f32(b200va_stager_t *s, const float *hA, const float *hB, float *hC,
                           size_t n, int variant, int mode);
 /* Device-side time of the last b200va_stager_add_f32 call, milliseconds (events). */
 int b200va_stager_last_ms(b200va_stager_t *s, float *ms);
+/* The mode the last b200va_stager_add_f32 call actually ran (after AUTO / fallbacks). */
+int b200va_stager_last_mode(b200va_stager_t *s, int *mode);
+/* Unregister every host range the stager page-locked (mode 4); call before freeing them
+ * if the stager outlives the arrays.  b200va_stager_destroy does this too. */
+int b200va_stager_release_host(b200va_stager_t *s);
 int b200va_stager_destroy(b200va_stager_t *s);
 /* One-shot convenience: create, add, destroy (synchronous). */
 int b200va_add_f32_host(const float *hA, const float *hB, float *hC, size_t n,
@@ -185,6 +232,8 @@ int b200va_host_free(void *p);
 int b200va_host_node_of(const void *p);
 /* NUMA node the current CUDA device is attached to, or -1. */
 int b200va_device_numa_node(void);
+/* Same for `device`, without making it current (no context is created). */
+int b200va_device_numa_node_of(int device);
 
 /* ---- generalised streaming element-wise core -------------------
  * The tuned 128-bit streaming skeleton of the vectorAdd kernel over other element types

@@ -15,6 +15,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200va.so")
+TUNE_LIB_PATH = os.path.join(_HERE, "libb200va_tune.so")   # same ABI, every b200va_tune_t combination (development)
 CLI_PATH = os.path.join(_HERE, "vectorAdd")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200va.h")
 
@@ -22,6 +23,8 @@ OK = 0
 ERR_INVALID, ERR_ALIGN, ERR_OVERLAP, ERR_VARIANT, ERR_NO_DEVICE, ERR_VERIFY, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 ERR_CUDA_BASE = -1000
 K_AUTO, K0_SCALAR, K1_VEC128, K2_TMA, K3_VEC256, K4_SCALAR_MLP = 0, 1, 2, 3, 4, 5
+F_INPUTS_STABLE = 1
+STAGE_AUTO, STAGE_SLOTS, STAGE_ZEROCOPY, STAGE_LANES, STAGE_BOUNCE, STAGE_REGISTER = -1, 0, 1, 2, 3, 4
 OPS = {"copy": 0, "scale": 1, "add": 2, "triad": 3}
 DTYPES = {"f32": 0, "f64": 1, "f16": 2, "bf16": 3}
 VARIANTS = {"auto": K_AUTO, "k0": K0_SCALAR, "k1": K1_VEC128, "k2": K2_TMA, "k3": K3_VEC256}
@@ -35,10 +38,25 @@ class B200VAError(RuntimeError):
 
 class Tune(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("kind", "threads", "unroll", "ctas_per_sm", "ld_hint", "st_hint",
-                                       "stages", "tile_bytes", "store_mode")]
+                                       "stages", "tile_bytes", "store_mode", "early_loads", "scheduler")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+    def kernel_name(self) -> str:
+        """The kernel this tune launches, as ncu prints it minus the (int)/(bool) casts: the key
+        of the per-kernel table in profiles/ncu_summary.json."""
+        if self.kind == K0_SCALAR:
+            return "vadd_scalar"
+        if self.kind == K2_TMA:
+            hint = int(self.ld_hint == 3)
+            if self.store_mode == 2:
+                return f"vadd_tma_clc<{hint},{self.st_hint}>"
+            return f"vadd_tma<{self.store_mode},{hint},{self.st_hint if self.store_mode == 0 else 0}>"
+        if self.kind == K4_SCALAR_MLP:
+            return f"vadd_scalar_unrolled<{self.unroll}>"
+        name = "vadd_vec_clc" if self.scheduler == 1 else "vadd_vec"
+        return f"{name}<{8 if self.kind == K3_VEC256 else 4},{self.unroll},{self.ld_hint},{self.st_hint},{self.early_loads}>"
 
 
 class DevInfo(C.Structure):
@@ -63,6 +81,7 @@ _SIGS = {
     "b200va_geometry": (_I, [C.POINTER(Tune), _SZ, _I, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "b200va_add_f32": (_I, [_P, _P, _P, _SZ, _I, _P]),
     "b200va_add_f32_tuned": (_I, [_P, _P, _P, _SZ, C.POINTER(Tune), _P]),
+    "b200va_add_f32_ex": (_I, [_P, _P, _P, _SZ, _I, C.c_uint, _P]),
     "b200va_add_f32_loop": (_I, [_P, _P, _P, _SZ, _I, _I, _I, _P]),
     "b200va_loop_create": (_I, [C.POINTER(_P), _P, _P, _P, _SZ, _I, _I]),
     "b200va_loop_run": (_I, [_P, _I, _P]),
@@ -76,6 +95,8 @@ _SIGS = {
     "b200va_stager_create": (_I, [C.POINTER(_P), _I, _SZ, _I]),
     "b200va_stager_add_f32": (_I, [_P, _P, _P, _P, _SZ, _I, _I]),
     "b200va_stager_last_ms": (_I, [_P, C.POINTER(C.c_float)]),
+    "b200va_stager_last_mode": (_I, [_P, C.POINTER(_I)]),
+    "b200va_stager_release_host": (_I, [_P]),
     "b200va_stager_destroy": (_I, [_P]),
     "b200va_add_f32_host": (_I, [_P, _P, _P, _SZ, _I, _I]),
     "b200va_host_alloc": (_I, [C.POINTER(_P), _SZ]),
@@ -83,14 +104,31 @@ _SIGS = {
     "b200va_host_free": (_I, [_P]),
     "b200va_host_node_of": (_I, [_P]),
     "b200va_device_numa_node": (_I, []),
+    "b200va_device_numa_node_of": (_I, [_I]),
     "b200va_stream": (_I, [_I, _I, _P, _P, _P, _SZ, C.c_double, _P]),
     "b200va_shard_range": (_I, [_SZ, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
 }
-for _name, (_res, _args) in _SIGS.items():
-    _f = getattr(lib, _name)          # AttributeError here = header/library mismatch
-    _f.restype, _f.argtypes = _res, _args
+def _bind(handle) -> None:
+    for _name, (_res, _args) in _SIGS.items():
+        _f = getattr(handle, _name)          # AttributeError here = header/library mismatch
+        _f.restype, _f.argtypes = _res, _args
 
+
+_bind(lib)
 EXPORTED = tuple(_SIGS)
+_tune_lib = None
+
+
+def tune_lib():
+    """libb200va_tune.so: the same C ABI with the full A/B matrix of b200va_tune_t compiled in
+    (the production library carries only what AUTO and the named variants resolve to)."""
+    global _tune_lib
+    if _tune_lib is None:
+        if not os.path.exists(TUNE_LIB_PATH):
+            raise ImportError(f"{TUNE_LIB_PATH} is missing: build it with `make -C {_HERE}`")
+        _tune_lib = C.CDLL(TUNE_LIB_PATH)
+        _bind(_tune_lib)
+    return _tune_lib
 
 
 def strerror(code: int) -> str:

@@ -76,7 +76,8 @@ int dev_info(int device, const b200va_devinfo_t** out)
         dc.info.sm_count = sms;
         dc.info.max_smem_optin = smem;
         dc.info.l2_bytes = l2;
-        dc.rc = (major == 10) ? B200VA_OK : B200VA_ERR_NO_DEVICE;
+        // the cubin is sm_100a SASS (+ compute_100a PTX): architecture-specific, it runs on CC 10.0 only
+        dc.rc = (major == 10 && minor == 0) ? B200VA_OK : B200VA_ERR_NO_DEVICE;
     });
     if (out) *out = &dc.info;
     return dc.rc;
@@ -90,54 +91,81 @@ int current_dev_info(const b200va_devinfo_t** out)
 }
 
 // ----------------------------------------------------------------------- vec dispatch
+// libb200va.so carries the production set only (what AUTO and the named variants resolve to,
+// plus close neighbours used by the parity tests); -DB200VA_TUNE_MATRIX (libb200va_tune.so, the
+// A/B tool's library) instantiates every combination of b200va_tune_t.  A combination that is
+// not compiled in makes the pick functions return nullptr -> B200VA_ERR_VARIANT.
 using vec_fn = void (*)(const float*, const float*, float*, size_t, size_t, size_t, size_t);
 
+template <int VW, int UNROLL, int LD, int ST>
+vec_fn pick_sched(int early, int sched)
+{
+    if (sched == 1) {
+#ifdef B200VA_TUNE_MATRIX
+        return early ? vadd_vec_clc<VW, UNROLL, LD, ST, true> : vadd_vec_clc<VW, UNROLL, LD, ST, false>;
+#else
+        if constexpr (VW == 4 && LD == LD_PLAIN && ST == ST_NA && (UNROLL == 2 || UNROLL == 4))
+            return early ? vadd_vec_clc<VW, UNROLL, LD, ST, true> : vadd_vec_clc<VW, UNROLL, LD, ST, false>;
+        else
+            return nullptr;
+#endif
+    }
+    return early ? vadd_vec<VW, UNROLL, LD, ST, true> : vadd_vec<VW, UNROLL, LD, ST, false>;
+}
+
 template <int VW, int UNROLL, int LD>
-vec_fn pick_st(int st)
+vec_fn pick_st(int st, int early, int sched)
 {
     switch (st) {
-        case ST_PLAIN: return vadd_vec<VW, UNROLL, LD, ST_PLAIN>;
-        case ST_NA:    return vadd_vec<VW, UNROLL, LD, ST_NA>;
-        case ST_CS:    return vadd_vec<VW, UNROLL, LD, ST_CS>;
-        case ST_NA_EF: return vadd_vec<VW, UNROLL, LD, ST_NA_EF>;
+        case ST_PLAIN: return pick_sched<VW, UNROLL, LD, ST_PLAIN>(early, sched);
+        case ST_NA:    return pick_sched<VW, UNROLL, LD, ST_NA>(early, sched);
+#ifdef B200VA_TUNE_MATRIX
+        case ST_CS:    return pick_sched<VW, UNROLL, LD, ST_CS>(early, sched);
+        case ST_NA_EF: return pick_sched<VW, UNROLL, LD, ST_NA_EF>(early, sched);
+#endif
     }
     return nullptr;
 }
 
 template <int VW, int UNROLL>
-vec_fn pick_ld(int ld, int st)
+vec_fn pick_ld(int ld, int st, int early, int sched)
 {
     switch (ld) {
-        case LD_PLAIN: return pick_st<VW, UNROLL, LD_PLAIN>(st);
-        case LD_NA:    return pick_st<VW, UNROLL, LD_NA>(st);
-        case LD_NC_NA: return pick_st<VW, UNROLL, LD_NC_NA>(st);
-        case LD_CS:    return pick_st<VW, UNROLL, LD_CS>(st);
-        case LD_NA_EF: return pick_st<VW, UNROLL, LD_NA_EF>(st);
-        case LD_NA_256: return pick_st<VW, UNROLL, LD_NA_256>(st);
+        case LD_PLAIN: return pick_st<VW, UNROLL, LD_PLAIN>(st, early, sched);
+        case LD_NA_EF: return pick_st<VW, UNROLL, LD_NA_EF>(st, early, sched);
+#ifdef B200VA_TUNE_MATRIX
+        case LD_NA:    return pick_st<VW, UNROLL, LD_NA>(st, early, sched);
+        case LD_NC_NA: return pick_st<VW, UNROLL, LD_NC_NA>(st, early, sched);
+        case LD_CS:    return pick_st<VW, UNROLL, LD_CS>(st, early, sched);
+        case LD_NA_256: return pick_st<VW, UNROLL, LD_NA_256>(st, early, sched);
+#endif
     }
     return nullptr;
 }
 
 template <int VW>
-vec_fn pick_unroll(int unroll, int ld, int st)
+vec_fn pick_unroll(int unroll, int ld, int st, int early, int sched)
 {
     switch (unroll) {
-        case 1: return pick_ld<VW, 1>(ld, st);
-        case 2: return pick_ld<VW, 2>(ld, st);
-        case 4: return pick_ld<VW, 4>(ld, st);
-        case 8: return pick_ld<VW, 8>(ld, st);
+        case 1: return pick_ld<VW, 1>(ld, st, early, sched);
+        case 2: return pick_ld<VW, 2>(ld, st, early, sched);
+        case 4: return pick_ld<VW, 4>(ld, st, early, sched);
+#ifdef B200VA_TUNE_MATRIX
+        case 8: return pick_ld<VW, 8>(ld, st, early, sched);
+#endif
     }
     return nullptr;
 }
 
-vec_fn pick_vec(int vw, int unroll, int ld, int st)
+vec_fn pick_vec(int vw, int unroll, int ld, int st, int early, int sched)
 {
-    return vw == 8 ? pick_unroll<8>(unroll, ld, st) : pick_unroll<4>(unroll, ld, st);
+    return vw == 8 ? pick_unroll<8>(unroll, ld, st, early, sched) : pick_unroll<4>(unroll, ld, st, early, sched);
 }
 
 // ----------------------------------------------------------------------- tma dispatch
 using tma_fn = void (*)(const float*, const float*, float*, size_t, size_t, size_t, uint32_t, uint32_t);
 
+#ifdef B200VA_TUNE_MATRIX
 template <int MODE, bool HINT>
 tma_fn pick_tma_st(int st)
 {
@@ -149,6 +177,7 @@ tma_fn pick_tma_st(int st)
     }
     return nullptr;
 }
+#endif
 
 template <bool HINT>
 tma_fn pick_tma_clc_st(int st)
@@ -156,8 +185,10 @@ tma_fn pick_tma_clc_st(int st)
     switch (st) {
         case ST_PLAIN: return vadd_tma_clc<HINT, ST_PLAIN>;
         case ST_NA:    return vadd_tma_clc<HINT, ST_NA>;
+#ifdef B200VA_TUNE_MATRIX
         case ST_CS:    return vadd_tma_clc<HINT, ST_CS>;
         case ST_NA_EF: return vadd_tma_clc<HINT, ST_NA_EF>;
+#endif
     }
     return nullptr;
 }
@@ -166,9 +197,16 @@ tma_fn pick_tma(int store_mode, bool l2_hint, int st)
 {
     if (store_mode == 2)  // cluster-launch-control tile scheduler, register stores
         return l2_hint ? pick_tma_clc_st<true>(st) : pick_tma_clc_st<false>(st);
+#ifdef B200VA_TUNE_MATRIX
     if (store_mode == 1)  // st hint is meaningless for bulk stores: one instantiation
         return l2_hint ? vadd_tma<1, true, ST_PLAIN> : vadd_tma<1, false, ST_PLAIN>;
     return l2_hint ? pick_tma_st<0, true>(st) : pick_tma_st<0, false>(st);
+#else
+    // the static-split ring (store modes 0/1) lost to the CLC form everywhere: tune library only
+    if (store_mode == 1 && !l2_hint) return vadd_tma<1, false, ST_PLAIN>;   // kept: the bulk-store (UBLKCP.G.S) form
+    if (store_mode == 0 && !l2_hint && st == ST_NA) return vadd_tma<0, false, ST_NA>;
+    return nullptr;
+#endif
 }
 
 std::mutex g_attr_mu;
@@ -309,9 +347,11 @@ int plan_geometry(const b200va_tune_t& t, const b200va_devinfo_t* di, size_t n, 
     if (t.threads < 32 || t.threads > 1024 || (t.threads & 31)) return B200VA_ERR_VARIANT;
     if (!is_pow2(t.unroll) || t.unroll > 8) return B200VA_ERR_VARIANT;
     if (t.ld_hint < 0 || t.ld_hint >= LD_HINTS || t.st_hint < 0 || t.st_hint >= ST_HINTS) return B200VA_ERR_VARIANT;
+    if (t.scheduler < 0 || t.scheduler > 1 || (t.scheduler == 1 && t.ctas_per_sm != 0)) return B200VA_ERR_VARIANT;
     const size_t tile_vecs = static_cast<size_t>(t.threads) * t.unroll;
     g->ntiles = (nvec + tile_vecs - 1) / tile_vecs;
     size_t grid = g->ntiles;
+    if (t.scheduler == 1 && grid > 0x7fffffffull) return B200VA_ERR_INVALID;   // CLC: one CTA per tile, 32-bit tile index
     if (t.ctas_per_sm > 0) {
         const size_t cap = static_cast<size_t>(di->sm_count) * t.ctas_per_sm;
         if (grid > cap) grid = cap;
@@ -434,7 +474,9 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
         return launch_kernel(fn, g.grid, g.block, g.smem, stream, dA, dB, dC, n, head, nvec,
                              static_cast<uint32_t>(t.tile_bytes), static_cast<uint32_t>(t.stages));
     }
-    vec_fn fn = pick_vec(vw, t.unroll, t.ld_hint, t.st_hint);
+    // early loads read A and B while the previous launch may still be running: never when C aliases an input
+    const int early = (t.early_loads && !aliased) ? 1 : 0;
+    vec_fn fn = pick_vec(vw, t.unroll, t.ld_hint, t.st_hint, early, t.scheduler);
     if (!fn) return B200VA_ERR_VARIANT;
     if (g.block > 512) RC_TRY(check_block_size(fn, g.block));   // deep unrolls: the CTA size is register-limited
     return launch_kernel(fn, g.grid, g.block, 0, stream, dA, dB, dC, n, head, nvec, g.ntiles);
@@ -487,7 +529,8 @@ int launch_stream_typed(const void* dA, const void* dB, void* dC, size_t n, doub
     } else if (m > (size_t{1} << 23)) { threads = 128; unroll = 2; }
     else if (m >= (size_t{1} << 21)) { threads = 256; unroll = 2; }
     else if (m >= (size_t{1} << 19)) { threads = 512; }
-    // development knob for profiles/: B200VA_STREAM_GEOMETRY="threads,unroll,skip_l1_stores"
+#ifdef B200VA_TUNE_MATRIX
+    // development knob for profiles/ (tune library only): B200VA_STREAM_GEOMETRY="threads,unroll,skip_l1_stores"
     static const struct Override { int threads = 0, unroll = 0, na = 0; } ov = [] {
         Override o;
         if (const char* e = std::getenv("B200VA_STREAM_GEOMETRY")) std::sscanf(e, "%d,%d,%d", &o.threads, &o.unroll, &o.na);
@@ -498,6 +541,7 @@ int launch_stream_typed(const void* dA, const void* dB, void* dC, size_t n, doub
         unroll = ov.unroll;
         skip_l1_stores = ov.na != 0;
     }
+#endif
     const size_t tile_vecs = static_cast<size_t>(threads) * unroll;
     size_t grid = (nvec + tile_vecs - 1) / tile_vecs;
     if (grid > 0x7fffffffull) grid = 0x7fffffffull;
@@ -505,12 +549,13 @@ int launch_stream_typed(const void* dA, const void* dB, void* dC, size_t n, doub
     const size_t ntiles = (nvec + tile_vecs - 1) / tile_vecs;
     using fn_t = void (*)(const void*, const void*, void*, size_t, size_t, size_t, size_t, S);
     fn_t fn = nullptr;
-    if (skip_l1_stores)
-        fn = unroll == 4 ? stream_vec<DT, OP, 4, LD_PLAIN, ST_NA> : unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_NA>
-                                                                                : stream_vec<DT, OP, 1, LD_PLAIN, ST_NA>;
-    else
-        fn = unroll == 4 ? stream_vec<DT, OP, 4, LD_PLAIN, ST_PLAIN> : unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_PLAIN>
-                                                                                   : stream_vec<DT, OP, 1, LD_PLAIN, ST_PLAIN>;
+#ifdef B200VA_TUNE_MATRIX
+    if (unroll == 4) fn = skip_l1_stores ? stream_vec<DT, OP, 4, LD_PLAIN, ST_NA> : stream_vec<DT, OP, 4, LD_PLAIN, ST_PLAIN>;
+#endif
+    if (!fn) {
+        if (skip_l1_stores) fn = unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_NA> : stream_vec<DT, OP, 1, LD_PLAIN, ST_NA>;
+        else fn = unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_PLAIN> : stream_vec<DT, OP, 1, LD_PLAIN, ST_PLAIN>;
+    }
     return launch_kernel(fn, static_cast<unsigned>(grid), threads, 0, st, dA, dB, dC, n, head, nvec, ntiles, s);
 }
 
@@ -594,6 +639,16 @@ int b200va_add_f32(const float* dA, const float* dB, float* dC, size_t n, int va
     return launch(dA, dB, dC, n, t, static_cast<cudaStream_t>(stream));
 }
 
+int b200va_add_f32_ex(const float* dA, const float* dB, float* dC, size_t n, int variant, unsigned flags, void* stream)
+{
+    if (variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
+    if (flags & ~B200VA_F_INPUTS_STABLE) return B200VA_ERR_INVALID;
+    b200va_tune_t t;
+    default_tune(variant, n, &t);
+    t.early_loads = (flags & B200VA_F_INPUTS_STABLE) ? 1 : 0;   // vec kernels only; ignored by K0/K2
+    return launch(dA, dB, dC, n, t, static_cast<cudaStream_t>(stream));
+}
+
 int b200va_add_f32_tuned(const float* dA, const float* dB, float* dC, size_t n,
                          const b200va_tune_t* tune, void* stream)
 {
@@ -610,6 +665,7 @@ int b200va_add_f32_tuned(const float* dA, const float* dB, float* dC, size_t n,
     if (t.unroll == 0) t.unroll = d.unroll ? d.unroll : 1;
     if (t.stages == 0) t.stages = d.stages;
     if (t.tile_bytes == 0) t.tile_bytes = d.tile_bytes;
+    if ((t.early_loads | t.scheduler) & ~1) return B200VA_ERR_VARIANT;
     return launch(dA, dB, dC, n, t, static_cast<cudaStream_t>(stream));
 }
 
@@ -630,7 +686,11 @@ static int capture_batch(b200va_loop* l, cudaStream_t cap)
 {
     CU_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
     int rc = B200VA_OK;
-    for (int i = 0; i < l->batch && rc == B200VA_OK; ++i) rc = launch(l->dA, l->dB, l->dC, l->n, l->tune, cap);
+    // node 0 follows an unknown predecessor; nodes 1.. follow the same add (which writes only C),
+    // so their loads may run ahead of the dependency (launch() drops the hint if C aliases A or B)
+    b200va_tune_t follow = l->tune;
+    follow.early_loads = 1;
+    for (int i = 0; i < l->batch && rc == B200VA_OK; ++i) rc = launch(l->dA, l->dB, l->dC, l->n, i ? follow : l->tune, cap);
     cudaGraph_t g = nullptr;
     const cudaError_t e = cudaStreamEndCapture(cap, &g);
     if (rc != B200VA_OK || e != cudaSuccess) {
@@ -692,10 +752,13 @@ int b200va_loop_run(b200va_loop_t* l, int iters, void* stream)
     if (!l || iters < 0) return B200VA_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int left = iters;
+    bool first = true;                       // the first launch of a run follows whatever the caller queued before
     if (l->exec) {
-        for (; left >= l->batch; left -= l->batch) CU_TRY(cudaGraphLaunch(l->exec, st));
+        for (; left >= l->batch; left -= l->batch) { CU_TRY(cudaGraphLaunch(l->exec, st)); first = false; }
     }
-    for (; left > 0; --left) RC_TRY(launch(l->dA, l->dB, l->dC, l->n, l->tune, st));
+    b200va_tune_t follow = l->tune;
+    follow.early_loads = 1;
+    for (; left > 0; --left) { RC_TRY(launch(l->dA, l->dB, l->dC, l->n, first ? l->tune : follow, st)); first = false; }
     return B200VA_OK;
 }
 
@@ -706,9 +769,11 @@ int b200va_add_f32_loop(const float* dA, const float* dB, float* dC, size_t n, i
     if (variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (graph_batch <= 1 || iters < graph_batch) {
-        b200va_tune_t t;
+        b200va_tune_t t, follow;
         default_tune(variant, n, &t);
-        for (int i = 0; i < iters; ++i) RC_TRY(launch(dA, dB, dC, n, t, st));
+        follow = t;
+        follow.early_loads = 1;
+        for (int i = 0; i < iters; ++i) RC_TRY(launch(dA, dB, dC, n, i ? follow : t, st));
         return B200VA_OK;
     }
     b200va_loop_t* l = nullptr;
@@ -847,12 +912,38 @@ int b200va_shard_range(size_t n, int world, int rank, size_t* begin, size_t* end
 }
 
 // ------------------------------------------------------------------ host-buffer path
+// Restores the calling thread's current device on every exit path of the entry points that
+// take a `device` argument (include/b200va.h: "restore the caller's current device").
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != device) err = cudaSetDevice(device);
+    }
+    ~DeviceGuard()
+    {
+        int now = -1;
+        if (prev >= 0 && cudaGetDevice(&now) == cudaSuccess && now != prev) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // Fork-join pool for the pageable path: T persistent workers, each copies one slice.
+// Construction may throw (std::system_error from std::thread under a pids limit, bad_alloc):
+// make_copy_pool() catches and degrades, nothing propagates through the C ABI.
 class CopyPool {
 public:
     explicit CopyPool(int threads) : n_(threads < 1 ? 1 : threads)
     {
-        for (int i = 1; i < n_; ++i) th_.emplace_back([this, i] { worker(i); });
+        th_.reserve(static_cast<size_t>(n_));
+        try {
+            for (int i = 1; i < n_; ++i) th_.emplace_back([this, i] { worker(i); });
+        } catch (...) {
+            n_ = static_cast<int>(th_.size()) + 1;          // run with the workers that did start
+        }
     }
     ~CopyPool()
     {
@@ -895,7 +986,7 @@ private:
                 seen = gen_;
                 if (stop_) return;
             }
-            slice(i);
+            if (i < n_) slice(i);
             std::lock_guard<std::mutex> lk(m_);
             if (--pending_ == 0) done_.notify_one();
         }
@@ -911,6 +1002,36 @@ private:
     const unsigned char* src_ = nullptr;
     size_t bytes_ = 0;
 };
+
+// Copy threads: the CPUs this process may use (affinity mask, cgroup v2 bandwidth quota), at
+// most 16; B200VA_COPY_THREADS overrides (clamped to 1..64).  Never throws: returns nullptr
+// only if even a single-threaded pool cannot be allocated.
+static CopyPool* make_copy_pool()
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) hw = static_cast<unsigned>(CPU_COUNT(&set));
+    if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[64];
+        double period = 0;
+        if (std::fscanf(f, "%63s %lf", q, &period) == 2 && std::strcmp(q, "max") != 0 && period > 0)
+            hw = std::min(hw, static_cast<unsigned>(std::max(1.0, std::atof(q) / period)));
+        std::fclose(f);
+    }
+    unsigned want = std::max(1u, std::min(16u, hw));
+    if (const char* e = std::getenv("B200VA_COPY_THREADS")) want = static_cast<unsigned>(std::min(64, std::max(1, std::atoi(e))));
+    for (; want >= 1; want /= 2) {
+        try {
+            return new CopyPool(static_cast<int>(want));
+        } catch (...) {
+            // bad_alloc / system_error while building the pool: retry smaller
+        }
+        if (want == 1) break;
+    }
+    return nullptr;
+}
+
+struct HostRange { uintptr_t lo, hi; };     // [lo, hi) page-locked by this stager (mode 4)
 
 struct b200va_stager {
     int device = 0;
@@ -928,16 +1049,18 @@ struct b200va_stager {
     float* bounce = nullptr;
     size_t bounce_chunk = 0;
     CopyPool* pool = nullptr;
+    // register-once path (mode 4): host ranges this stager page-locked
+    std::vector<HostRange>* regs = nullptr;
     float last_ms = 0.f;
+    int last_mode = -1;
 };
 
-// NUMA node the current CUDA device hangs off (sysfs), or -1.  B200VA_NUMA_NODE overrides.
-static int device_numa_node()
+// NUMA node a CUDA device hangs off (sysfs), or -1.  B200VA_NUMA_NODE overrides.
+static int device_numa_node_of(int dev)
 {
     if (const char* e = std::getenv("B200VA_NUMA_NODE")) return std::atoi(e);
-    int dev = 0;
     char bus[32] = {0}, path[128];
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) { cudaGetLastError(); return -1; }
     for (char* c = bus; *c; ++c) *c = static_cast<char>(std::tolower(*c));
     std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
     int node = -1;
@@ -946,6 +1069,13 @@ static int device_numa_node()
         std::fclose(f);
     }
     return node;
+}
+
+static int device_numa_node()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return device_numa_node_of(dev);
 }
 
 // Parses a sysfs cpulist ("0-31,64-95") into a cpu_set_t restricted to `allowed`.
@@ -975,16 +1105,20 @@ static bool node_cpuset(int node, const cpu_set_t& allowed, cpu_set_t* out)
 // Pinned, mapped host memory whose pages sit on the NUMA node local to the current GPU:
 // the calling thread is moved onto that node's CPUs (and its memory policy set to prefer
 // the node) for the duration of the allocation, so the first touch inside cudaHostAlloc
-// lands there; a PCIe DMA then never crosses the inter-socket link.
+// lands there; a PCIe DMA then never crosses the inter-socket link.  Affinity and memory
+// policy of the caller (e.g. numactl --interleave) are saved and put back.
 int b200va_host_alloc_ex(void** out, size_t bytes, int write_combined)
 {
     if (!out) return B200VA_ERR_INVALID;
     const int node = device_numa_node();
     cpu_set_t old_set, node_set;
     bool moved = false, policy = false;
+    int old_mode = 0;
+    unsigned long old_mask[16] = {0};                       // 1024 nodes
+    constexpr unsigned long kMaxNode = sizeof old_mask * 8;
     if (node >= 0 && sched_getaffinity(0, sizeof old_set, &old_set) == 0 && node_cpuset(node, old_set, &node_set)) {
         moved = sched_setaffinity(0, sizeof node_set, &node_set) == 0;
-        if (node < 64) {
+        if (node < 64 && syscall(SYS_get_mempolicy, &old_mode, old_mask, kMaxNode, nullptr, 0ul) == 0) {
             unsigned long mask = 1ul << node;
             policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0;
         }
@@ -992,7 +1126,12 @@ int b200va_host_alloc_ex(void** out, size_t bytes, int write_combined)
     unsigned flags = cudaHostAllocPortable | cudaHostAllocMapped;
     if (write_combined) flags |= cudaHostAllocWriteCombined;   // H2D sources only: CPU reads of WC memory crawl
     const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, flags);
-    if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+    if (policy) {
+        bool any = false;
+        for (unsigned long w : old_mask) any = any || w != 0;
+        if (syscall(SYS_set_mempolicy, old_mode, any ? old_mask : nullptr, any ? kMaxNode : 0ul) != 0)
+            syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+    }
     if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
     CU_TRY(e);
     return B200VA_OK;
@@ -1002,6 +1141,7 @@ int b200va_host_alloc(void** out, size_t bytes) { return b200va_host_alloc_ex(ou
 
 // NUMA node the current CUDA device is attached to (sysfs), or -1.
 int b200va_device_numa_node(void) { return device_numa_node(); }
+int b200va_device_numa_node_of(int device) { return device_numa_node_of(device); }
 
 // NUMA node holding the page at `p` (get_mempolicy(MPOL_F_NODE | MPOL_F_ADDR)), or -1.
 int b200va_host_node_of(const void* p)
@@ -1019,12 +1159,28 @@ int b200va_host_free(void* p)
     return B200VA_OK;
 }
 
+static void stager_release_host(b200va_stager* s)
+{
+    if (!s->regs) return;
+    for (const HostRange& r : *s->regs)
+        if (cudaHostUnregister(reinterpret_cast<void*>(r.lo)) != cudaSuccess) cudaGetLastError();
+    s->regs->clear();
+}
+
+int b200va_stager_release_host(b200va_stager_t* s)
+{
+    if (!s) return B200VA_ERR_INVALID;
+    DeviceGuard g(s->device);
+    stager_release_host(s);
+    return B200VA_OK;
+}
+
 int b200va_stager_destroy(b200va_stager_t* s)
 {
     if (!s) return B200VA_OK;
-    int prev = -1;
-    cudaGetDevice(&prev);
-    cudaSetDevice(s->device);
+    DeviceGuard g(s->device);
+    stager_release_host(s);
+    delete s->regs;
     if (s->slot) {
         for (int i = 0; i < s->depth; ++i) {
             if (s->slot[i]) cudaStreamDestroy(s->slot[i]);
@@ -1048,7 +1204,6 @@ int b200va_stager_destroy(b200va_stager_t* s)
     delete[] s->slot;
     delete[] s->slot_done;
     delete s;
-    if (prev >= 0) cudaSetDevice(prev);
     return B200VA_OK;
 }
 
@@ -1061,7 +1216,8 @@ int b200va_stager_create(b200va_stager_t** out, int device, size_t chunk_elems, 
     if (depth < 1 || depth > 16) return B200VA_ERR_INVALID;
     chunk_elems = (chunk_elems + 63) & ~size_t{63};        // slots stay 256-B aligned
     RC_TRY(dev_info(device, nullptr));
-    CU_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CU_TRY(guard.err);
     b200va_stager* s = new (std::nothrow) b200va_stager;
     if (!s) return B200VA_ERR_NOMEM;
     s->device = device;
@@ -1069,7 +1225,8 @@ int b200va_stager_create(b200va_stager_t** out, int device, size_t chunk_elems, 
     s->depth = depth;
     s->slot = new (std::nothrow) cudaStream_t[depth]();
     s->slot_done = new (std::nothrow) cudaEvent_t[depth]();
-    if (!s->slot || !s->slot_done) { b200va_stager_destroy(s); return B200VA_ERR_NOMEM; }
+    s->regs = new (std::nothrow) std::vector<HostRange>();
+    if (!s->slot || !s->slot_done || !s->regs) { b200va_stager_destroy(s); return B200VA_ERR_NOMEM; }
     cudaError_t e = cudaMalloc(&s->d_buf, static_cast<size_t>(depth) * 3 * chunk_elems * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->main, cudaStreamNonBlocking);
     for (int i = 0; i < depth && e == cudaSuccess; ++i) {
@@ -1094,162 +1251,231 @@ int b200va_stager_create(b200va_stager_t** out, int device, size_t chunk_elems, 
     return B200VA_OK;
 }
 
+// ---- the pipelines (device already current; a non-OK return leaves work in flight: the caller drains)
+static int stage_zero_copy(b200va_stager* s, const float* hA, const float* hB, float* hC, size_t n, int variant)
+{
+    // the kernel streams A and B from pinned host memory over PCIe and writes C back the same
+    // way -- both link directions busy, no staging latency.
+    const float *dA = nullptr, *dB = nullptr;
+    float* dC = nullptr;
+    if (n) {
+        CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(const_cast<float**>(&dA)), const_cast<float*>(hA), 0));
+        CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(const_cast<float**>(&dB)), const_cast<float*>(hB), 0));
+        CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dC), hC, 0));
+    }
+    b200va_tune_t t;
+    default_tune(variant == B200VA_K_AUTO ? B200VA_K1_VEC128 : variant, n, &t);
+    return launch(dA, dB, dC, n, t, s->main);
+}
+
+static int stage_slots(b200va_stager* s, const float* hA, const float* hB, float* hC, size_t n, int variant)
+{
+    const size_t nchunks = (n + s->chunk - 1) / s->chunk;
+    for (int i = 0; i < s->depth; ++i) CU_TRY(cudaStreamWaitEvent(s->slot[i], s->ev_start, 0));
+    b200va_tune_t t;
+    for (size_t k = 0; k < nchunks; ++k) {
+        const int i = static_cast<int>(k % static_cast<size_t>(s->depth));
+        const size_t off = k * s->chunk;
+        const size_t m = (n - off < s->chunk) ? n - off : s->chunk;
+        float* dA = s->d_buf + static_cast<size_t>(i) * 3 * s->chunk;
+        float* dB = dA + s->chunk;
+        float* dC = dB + s->chunk;
+        CU_TRY(cudaMemcpyAsync(dA, hA + off, m * sizeof(float), cudaMemcpyHostToDevice, s->slot[i]));
+        CU_TRY(cudaMemcpyAsync(dB, hB + off, m * sizeof(float), cudaMemcpyHostToDevice, s->slot[i]));
+        default_tune(variant, m, &t);
+        RC_TRY(launch(dA, dB, dC, m, t, s->slot[i]));
+        CU_TRY(cudaMemcpyAsync(hC + off, dC, m * sizeof(float), cudaMemcpyDeviceToHost, s->slot[i]));
+    }
+    for (int i = 0; i < s->depth; ++i) {
+        CU_TRY(cudaEventRecord(s->slot_done[i], s->slot[i]));
+        CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[i], 0));
+    }
+    return B200VA_OK;
+}
+
+static int stage_lanes(b200va_stager* s, const float* hA, const float* hB, float* hC, size_t n, int variant)
+{
+    // lanes: every H2D copy queues on one stream, every add on a second, every D2H on a
+    // third; slot reuse and data flow are event edges.  The H2D queue -- the bottleneck
+    // direction -- never waits behind a kernel or a D2H of another chunk.
+    for (cudaStream_t st : {s->lane_h2d, s->lane_k, s->lane_d2h}) CU_TRY(cudaStreamWaitEvent(st, s->ev_start, 0));
+    b200va_tune_t t;
+    // Full-size chunks, then a tapered tail (1/2, 1/4, ... down to ~1 Mi elements): what is left
+    // after the last H2D byte has arrived is one small add and one small D2H, not a full chunk.
+    const size_t taper_min = size_t{1} << 20;
+    size_t off = 0;
+    for (size_t k = 0; off < n; ++k) {
+        const size_t left = n - off;
+        size_t m = s->chunk;
+        if (left <= s->chunk && s->depth > 1) {
+            m = left / 2;
+            m = (m + 63) & ~size_t{63};                      // chunk starts stay 256-byte aligned
+            if (m < taper_min || m >= left) m = left;
+        }
+        if (m > left) m = left;
+        const int i = static_cast<int>(k % static_cast<size_t>(s->depth));
+        float* dA = s->d_buf + static_cast<size_t>(i) * 3 * s->chunk;
+        float* dB = dA + s->chunk;
+        float* dC = dB + s->chunk;
+        if (k >= static_cast<size_t>(s->depth)) CU_TRY(cudaStreamWaitEvent(s->lane_h2d, s->ev_out[i], 0));  // slot drained
+        CU_TRY(cudaMemcpyAsync(dA, hA + off, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
+        CU_TRY(cudaMemcpyAsync(dB, hB + off, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
+        CU_TRY(cudaEventRecord(s->ev_in[i], s->lane_h2d));
+        CU_TRY(cudaStreamWaitEvent(s->lane_k, s->ev_in[i], 0));
+        default_tune(variant, m, &t);
+        RC_TRY(launch(dA, dB, dC, m, t, s->lane_k));
+        CU_TRY(cudaEventRecord(s->ev_sum[i], s->lane_k));
+        CU_TRY(cudaStreamWaitEvent(s->lane_d2h, s->ev_sum[i], 0));
+        CU_TRY(cudaMemcpyAsync(hC + off, dC, m * sizeof(float), cudaMemcpyDeviceToHost, s->lane_d2h));
+        CU_TRY(cudaEventRecord(s->ev_out[i], s->lane_d2h));
+        off += m;
+    }
+    CU_TRY(cudaEventRecord(s->slot_done[0], s->lane_d2h));   // the D2H lane finishes last
+    CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[0], 0));
+    return B200VA_OK;
+}
+
+static int stage_bounce(b200va_stager* s, const float* hA, const float* hB, float* hC, size_t n, int variant)
+{
+    // Pageable host arrays (plain malloc, what one ./vectorAdd process has): a cudaMemcpy from
+    // pageable memory is staged by the driver on one thread at ~10 GB/s.  Here a pool of host
+    // threads copies chunk k+1 into pinned bounce buffers and chunk k-2 out of them while the
+    // copy engines and the add work on the chunks in between (lanes as in mode 2).
+    const size_t bc = std::min(s->chunk, size_t{1} << 23);          // 32 MiB bounce chunks
+    if (!s->pool) {
+        s->pool = make_copy_pool();
+        if (!s->pool) return B200VA_ERR_NOMEM;
+    }
+    if (!s->bounce || s->bounce_chunk != bc) {
+        if (s->bounce) { cudaFreeHost(s->bounce); s->bounce = nullptr; }
+        void* p = nullptr;
+        RC_TRY(b200va_host_alloc(&p, static_cast<size_t>(s->depth) * 3 * bc * sizeof(float)));
+        s->bounce = static_cast<float*>(p);
+        s->bounce_chunk = bc;
+    }
+    for (cudaStream_t st : {s->lane_h2d, s->lane_k, s->lane_d2h}) CU_TRY(cudaStreamWaitEvent(st, s->ev_start, 0));
+    const size_t nchunks = (n + bc - 1) / bc;
+    const size_t depth = static_cast<size_t>(s->depth);
+    b200va_tune_t t;
+    auto span = [&](size_t k, size_t* off, size_t* m) { *off = k * bc; *m = std::min(bc, n - *off); };
+    for (size_t k = 0; k < nchunks + depth - 1 || k < nchunks; ++k) {
+        if (k < nchunks) {
+            size_t off, m;
+            span(k, &off, &m);
+            const size_t i = k % depth;
+            float* pA = s->bounce + i * 3 * bc;
+            float* dA = s->d_buf + i * 3 * s->chunk;
+            // slot i was drained (copied out) at iteration k-1 below, or never used
+            s->pool->copy(pA, hA + off, m * sizeof(float));
+            s->pool->copy(pA + bc, hB + off, m * sizeof(float));
+            CU_TRY(cudaMemcpyAsync(dA, pA, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
+            CU_TRY(cudaMemcpyAsync(dA + s->chunk, pA + bc, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
+            CU_TRY(cudaEventRecord(s->ev_in[i], s->lane_h2d));
+            CU_TRY(cudaStreamWaitEvent(s->lane_k, s->ev_in[i], 0));
+            default_tune(variant, m, &t);
+            RC_TRY(launch(dA, dA + s->chunk, dA + 2 * s->chunk, m, t, s->lane_k));
+            CU_TRY(cudaEventRecord(s->ev_sum[i], s->lane_k));
+            CU_TRY(cudaStreamWaitEvent(s->lane_d2h, s->ev_sum[i], 0));
+            CU_TRY(cudaMemcpyAsync(pA + 2 * bc, dA + 2 * s->chunk, m * sizeof(float), cudaMemcpyDeviceToHost, s->lane_d2h));
+            CU_TRY(cudaEventRecord(s->ev_out[i], s->lane_d2h));
+        }
+        if (k + 1 >= depth) {                                       // retire chunk j = k - (depth - 1)
+            const size_t j = k + 1 - depth;
+            if (j < nchunks) {
+                size_t off, m;
+                span(j, &off, &m);
+                const size_t i = j % depth;
+                CU_TRY(cudaEventSynchronize(s->ev_out[i]));
+                s->pool->copy(hC + off, s->bounce + i * 3 * bc + 2 * bc, m * sizeof(float));
+            }
+        }
+    }
+    CU_TRY(cudaEventRecord(s->slot_done[0], s->lane_d2h));
+    CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[0], 0));
+    return B200VA_OK;
+}
+
+static bool host_is_pinned(const void* p)
+{
+    cudaPointerAttributes at{};
+    const bool ok = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+    if (!ok) cudaGetLastError();
+    return ok;
+}
+
+// Page-locks [p, p+bytes) in place unless the runtime already knows it (cudaHostAlloc'd,
+// registered by the caller, or by this stager earlier).  Returns false if the range cannot be
+// registered -- the caller then falls back to the bounce path.
+static bool ensure_registered(b200va_stager* s, const void* p, size_t bytes)
+{
+    if (bytes == 0) return true;
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p), hi = lo + bytes;
+    for (const HostRange& r : *s->regs)
+        if (r.lo <= lo && hi <= r.hi) return true;                  // cached
+    if (host_is_pinned(p) && host_is_pinned(reinterpret_cast<const void*>(hi - 1))) return true;
+    // a cached range that overlaps without containing the new one (the caller's buffer moved or grew): drop it
+    for (size_t i = 0; i < s->regs->size();) {
+        const HostRange r = (*s->regs)[i];
+        if (r.lo < hi && lo < r.hi) {
+            if (cudaHostUnregister(reinterpret_cast<void*>(r.lo)) != cudaSuccess) cudaGetLastError();
+            s->regs->erase(s->regs->begin() + static_cast<long>(i));
+        } else {
+            ++i;
+        }
+    }
+    const cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    try {
+        s->regs->push_back(HostRange{lo, hi});
+    } catch (...) {
+        cudaHostUnregister(const_cast<void*>(p));
+        return false;
+    }
+    return true;
+}
+
+static void stager_drain(b200va_stager* s)
+{
+    // after a failure in the middle of a pipeline: nothing may still be reading or writing the
+    // caller's arrays (or the bounce ring) when the error code is returned
+    for (int i = 0; i < s->depth; ++i)
+        if (s->slot && s->slot[i]) cudaStreamSynchronize(s->slot[i]);
+    for (cudaStream_t st : {s->lane_h2d, s->lane_k, s->lane_d2h, s->main})
+        if (st) cudaStreamSynchronize(st);
+    cudaGetLastError();
+}
+
 int b200va_stager_add_f32(b200va_stager_t* s, const float* hA, const float* hB, float* hC, size_t n,
                           int variant, int mode)
 {
     if (!s || (n && (!hA || !hB || !hC))) return B200VA_ERR_INVALID;
     if (variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
-    CU_TRY(cudaSetDevice(s->device));
-    CU_TRY(cudaEventRecord(s->ev_start, s->main));
-    if (mode == 1) {
-        // zero-copy: the kernel streams A and B from pinned host memory over PCIe and
-        // writes C back the same way -- both link directions busy, no staging latency.
-        const float *dA = nullptr, *dB = nullptr;
-        float* dC = nullptr;
-        if (n) {
-            CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(const_cast<float**>(&dA)),
-                                            const_cast<float*>(hA), 0));
-            CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(const_cast<float**>(&dB)),
-                                            const_cast<float*>(hB), 0));
-            CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dC), hC, 0));
-        }
-        b200va_tune_t t;
-        default_tune(variant == B200VA_K_AUTO ? B200VA_K1_VEC128 : variant, n, &t);
-        RC_TRY(launch(dA, dB, dC, n, t, s->main));
-    } else if (mode == 0) {
-        const size_t nchunks = (n + s->chunk - 1) / s->chunk;
-        for (int i = 0; i < s->depth; ++i) CU_TRY(cudaStreamWaitEvent(s->slot[i], s->ev_start, 0));
-        b200va_tune_t t;
-        for (size_t k = 0; k < nchunks; ++k) {
-            const int i = static_cast<int>(k % static_cast<size_t>(s->depth));
-            const size_t off = k * s->chunk;
-            const size_t m = (n - off < s->chunk) ? n - off : s->chunk;
-            float* dA = s->d_buf + static_cast<size_t>(i) * 3 * s->chunk;
-            float* dB = dA + s->chunk;
-            float* dC = dB + s->chunk;
-            CU_TRY(cudaMemcpyAsync(dA, hA + off, m * sizeof(float), cudaMemcpyHostToDevice, s->slot[i]));
-            CU_TRY(cudaMemcpyAsync(dB, hB + off, m * sizeof(float), cudaMemcpyHostToDevice, s->slot[i]));
-            default_tune(variant, m, &t);
-            RC_TRY(launch(dA, dB, dC, m, t, s->slot[i]));
-            CU_TRY(cudaMemcpyAsync(hC + off, dC, m * sizeof(float), cudaMemcpyDeviceToHost, s->slot[i]));
-        }
-        for (int i = 0; i < s->depth; ++i) {
-            CU_TRY(cudaEventRecord(s->slot_done[i], s->slot[i]));
-            CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[i], 0));
-        }
-    } else if (mode == 2) {
-        // lanes: every H2D copy queues on one stream, every add on a second, every D2H on a
-        // third; slot reuse and data flow are event edges.  The H2D queue -- the bottleneck
-        // direction -- never waits behind a kernel or a D2H of another chunk.
-        for (cudaStream_t st : {s->lane_h2d, s->lane_k, s->lane_d2h}) CU_TRY(cudaStreamWaitEvent(st, s->ev_start, 0));
-        b200va_tune_t t;
-        // Full-size chunks, then a tapered tail (1/2, 1/4, ... down to ~1 Mi elements): what is left
-        // after the last H2D byte has arrived is one small add and one small D2H, not a full chunk.
-        const size_t taper_min = size_t{1} << 20;
-        size_t off = 0;
-        for (size_t k = 0; off < n; ++k) {
-            const size_t left = n - off;
-            size_t m = s->chunk;
-            if (left <= s->chunk && s->depth > 1) {
-                m = left / 2;
-                m = (m + 63) & ~size_t{63};                      // chunk starts stay 256-byte aligned
-                if (m < taper_min || m >= left) m = left;
-            }
-            if (m > left) m = left;
-            const int i = static_cast<int>(k % static_cast<size_t>(s->depth));
-            float* dA = s->d_buf + static_cast<size_t>(i) * 3 * s->chunk;
-            float* dB = dA + s->chunk;
-            float* dC = dB + s->chunk;
-            if (k >= static_cast<size_t>(s->depth)) CU_TRY(cudaStreamWaitEvent(s->lane_h2d, s->ev_out[i], 0));  // slot drained
-            CU_TRY(cudaMemcpyAsync(dA, hA + off, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
-            CU_TRY(cudaMemcpyAsync(dB, hB + off, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
-            CU_TRY(cudaEventRecord(s->ev_in[i], s->lane_h2d));
-            CU_TRY(cudaStreamWaitEvent(s->lane_k, s->ev_in[i], 0));
-            default_tune(variant, m, &t);
-            RC_TRY(launch(dA, dB, dC, m, t, s->lane_k));
-            CU_TRY(cudaEventRecord(s->ev_sum[i], s->lane_k));
-            CU_TRY(cudaStreamWaitEvent(s->lane_d2h, s->ev_sum[i], 0));
-            CU_TRY(cudaMemcpyAsync(hC + off, dC, m * sizeof(float), cudaMemcpyDeviceToHost, s->lane_d2h));
-            CU_TRY(cudaEventRecord(s->ev_out[i], s->lane_d2h));
-            off += m;
-        }
-        CU_TRY(cudaEventRecord(s->slot_done[0], s->lane_d2h));   // the D2H lane finishes last
-        CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[0], 0));
-    } else if (mode == 3) {
-        // Pageable host arrays (plain malloc, what one ./vectorAdd process has): a cudaMemcpy from
-        // pageable memory is staged by the driver on one thread at ~10 GB/s.  Here a pool of host
-        // threads copies chunk k+1 into pinned bounce buffers and chunk k-2 out of them while the
-        // copy engines and the add work on the chunks in between (lanes as in mode 2).
-        const size_t bc = std::min(s->chunk, size_t{1} << 23);          // 32 MiB bounce chunks
-        if (!s->pool) {
-            // copy threads: the CPUs this process may use (affinity mask, cgroup v2 bandwidth quota), at most 16;
-            // B200VA_COPY_THREADS overrides
-            unsigned hw = std::thread::hardware_concurrency();
-            cpu_set_t set;
-            if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) hw = static_cast<unsigned>(CPU_COUNT(&set));
-            if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
-                char q[64];
-                double period = 0;
-                if (std::fscanf(f, "%63s %lf", q, &period) == 2 && std::strcmp(q, "max") != 0 && period > 0)
-                    hw = std::min(hw, static_cast<unsigned>(std::max(1.0, std::atof(q) / period)));
-                std::fclose(f);
-            }
-            unsigned want = std::max(1u, std::min(16u, hw));
-            if (const char* e = std::getenv("B200VA_COPY_THREADS")) want = static_cast<unsigned>(std::max(1, std::atoi(e)));
-            s->pool = new (std::nothrow) CopyPool(static_cast<int>(want));
-            if (!s->pool) return B200VA_ERR_NOMEM;
-        }
-        if (!s->bounce || s->bounce_chunk != bc) {
-            if (s->bounce) { cudaFreeHost(s->bounce); s->bounce = nullptr; }
-            void* p = nullptr;
-            RC_TRY(b200va_host_alloc(&p, static_cast<size_t>(s->depth) * 3 * bc * sizeof(float)));
-            s->bounce = static_cast<float*>(p);
-            s->bounce_chunk = bc;
-        }
-        for (cudaStream_t st : {s->lane_h2d, s->lane_k, s->lane_d2h}) CU_TRY(cudaStreamWaitEvent(st, s->ev_start, 0));
-        const size_t nchunks = (n + bc - 1) / bc;
-        const size_t depth = static_cast<size_t>(s->depth);
-        b200va_tune_t t;
-        auto span = [&](size_t k, size_t* off, size_t* m) { *off = k * bc; *m = std::min(bc, n - *off); };
-        for (size_t k = 0; k < nchunks + depth - 1 || k < nchunks; ++k) {
-            if (k < nchunks) {
-                size_t off, m;
-                span(k, &off, &m);
-                const size_t i = k % depth;
-                float* pA = s->bounce + i * 3 * bc;
-                float* dA = s->d_buf + i * 3 * s->chunk;
-                // slot i was drained (copied out) at iteration k-1 below, or never used
-                s->pool->copy(pA, hA + off, m * sizeof(float));
-                s->pool->copy(pA + bc, hB + off, m * sizeof(float));
-                CU_TRY(cudaMemcpyAsync(dA, pA, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
-                CU_TRY(cudaMemcpyAsync(dA + s->chunk, pA + bc, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
-                CU_TRY(cudaEventRecord(s->ev_in[i], s->lane_h2d));
-                CU_TRY(cudaStreamWaitEvent(s->lane_k, s->ev_in[i], 0));
-                default_tune(variant, m, &t);
-                RC_TRY(launch(dA, dA + s->chunk, dA + 2 * s->chunk, m, t, s->lane_k));
-                CU_TRY(cudaEventRecord(s->ev_sum[i], s->lane_k));
-                CU_TRY(cudaStreamWaitEvent(s->lane_d2h, s->ev_sum[i], 0));
-                CU_TRY(cudaMemcpyAsync(pA + 2 * bc, dA + 2 * s->chunk, m * sizeof(float), cudaMemcpyDeviceToHost, s->lane_d2h));
-                CU_TRY(cudaEventRecord(s->ev_out[i], s->lane_d2h));
-            }
-            if (k + 1 >= depth) {                                       // retire chunk j = k - (depth - 1)
-                const size_t j = k + 1 - depth;
-                if (j < nchunks) {
-                    size_t off, m;
-                    span(j, &off, &m);
-                    const size_t i = j % depth;
-                    CU_TRY(cudaEventSynchronize(s->ev_out[i]));
-                    s->pool->copy(hC + off, s->bounce + i * 3 * bc + 2 * bc, m * sizeof(float));
-                }
-            }
-        }
-        CU_TRY(cudaEventRecord(s->slot_done[0], s->lane_d2h));
-        CU_TRY(cudaStreamWaitEvent(s->main, s->slot_done[0], 0));
-    } else {
-        return B200VA_ERR_INVALID;
+    if (mode < B200VA_STAGE_AUTO || mode > B200VA_STAGE_REGISTER) return B200VA_ERR_INVALID;
+    DeviceGuard guard(s->device);
+    CU_TRY(guard.err);
+    const size_t bytes = n * sizeof(float);
+    if (mode == B200VA_STAGE_AUTO) {
+        const bool pinned = n == 0 || (host_is_pinned(hA) && host_is_pinned(hB) && host_is_pinned(hC));
+        mode = pinned ? B200VA_STAGE_LANES : (3 * bytes >= (size_t{8} << 20) ? B200VA_STAGE_REGISTER : B200VA_STAGE_BOUNCE);
     }
-    CU_TRY(cudaEventRecord(s->ev_stop, s->main));
-    CU_TRY(cudaStreamSynchronize(s->main));
+    if (mode == B200VA_STAGE_REGISTER) {
+        // page-lock the caller's arrays once (outside the timed pipeline: it is a one-off cost of the first call)
+        const bool ok = ensure_registered(s, hA, bytes) && ensure_registered(s, hB, bytes) && ensure_registered(s, hC, bytes);
+        if (!ok) mode = B200VA_STAGE_BOUNCE;
+    }
+    s->last_mode = mode;
+    CU_TRY(cudaEventRecord(s->ev_start, s->main));
+    int rc = B200VA_OK;
+    switch (mode) {
+        case B200VA_STAGE_ZEROCOPY: rc = stage_zero_copy(s, hA, hB, hC, n, variant); break;
+        case B200VA_STAGE_SLOTS:    rc = stage_slots(s, hA, hB, hC, n, variant); break;
+        case B200VA_STAGE_LANES:
+        case B200VA_STAGE_REGISTER: rc = stage_lanes(s, hA, hB, hC, n, variant); break;
+        case B200VA_STAGE_BOUNCE:   rc = stage_bounce(s, hA, hB, hC, n, variant); break;
+    }
+    if (rc == B200VA_OK) rc = cuda_err(cudaEventRecord(s->ev_stop, s->main));
+    if (rc == B200VA_OK) rc = cuda_err(cudaStreamSynchronize(s->main));
+    if (rc != B200VA_OK) { stager_drain(s); return rc; }
     CU_TRY(cudaEventElapsedTime(&s->last_ms, s->ev_start, s->ev_stop));
     return B200VA_OK;
 }
@@ -1261,22 +1487,28 @@ int b200va_stager_last_ms(b200va_stager_t* s, float* ms)
     return B200VA_OK;
 }
 
+int b200va_stager_last_mode(b200va_stager_t* s, int* mode)
+{
+    if (!s || !mode) return B200VA_ERR_INVALID;
+    *mode = s->last_mode;
+    return B200VA_OK;
+}
+
 int b200va_add_f32_host(const float* hA, const float* hB, float* hC, size_t n, int device, int variant)
 {
     b200va_stager_t* s = nullptr;
     size_t chunk = size_t{1} << 25;
     if (n < chunk) chunk = n ? n : 1;
+    RC_TRY(dev_info(device, nullptr));
+    DeviceGuard guard(device);          // cudaPointerGetAttributes below needs a current device; restored on return
+    CU_TRY(guard.err);
     // pinned/registered arrays go straight to the copy engines; pageable ones through the bounce pool
-    bool pageable = false;
-    for (const void* p : {static_cast<const void*>(hA), static_cast<const void*>(hB), static_cast<const void*>(hC)}) {
-        cudaPointerAttributes at{};
-        if (n && (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type == cudaMemoryTypeUnregistered)) pageable = true;
-    }
-    cudaGetLastError();
-    // one-shot: pinning the bounce ring costs ~0.35 ms/MiB, so keep it small (9 x 8 MiB)
+    // (one-shot: page-locking 3 arrays for a single pass costs more than bouncing them)
+    const bool pageable = n && !(host_is_pinned(hA) && host_is_pinned(hB) && host_is_pinned(hC));
+    // pinning the bounce ring costs ~0.35 ms/MiB, so keep it small (9 x 8 MiB)
     if (pageable && chunk > (size_t{1} << 21)) chunk = size_t{1} << 21;
     RC_TRY(b200va_stager_create(&s, device, chunk, n > chunk ? 3 : 1));
-    const int rc = b200va_stager_add_f32(s, hA, hB, hC, n, variant, pageable ? 3 : 2);
+    const int rc = b200va_stager_add_f32(s, hA, hB, hC, n, variant, pageable ? B200VA_STAGE_BOUNCE : B200VA_STAGE_LANES);
     b200va_stager_destroy(s);
     return rc;
 }

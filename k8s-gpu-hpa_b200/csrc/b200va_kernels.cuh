@@ -13,6 +13,15 @@
 //                        array in flight, cache-hinted, tile-strided (optionally
 //                        persistent).
 //   K3  vadd_vec<8,...>  same with 256-bit LDG.E.256/STG.E.256 (PTX 8.8, sm_100).
+//   K1c vadd_vec_clc     the K1/K3 tile body with Blackwell's cluster-launch-control
+//                        scheduler: resident CTAs cancel not-yet-started CTAs of the grid
+//                        and take over their tiles (no CTA relaunch per tile).
+//   EARLY (K1/K3/K1c)    the loads of a CTA's first tile are issued BEFORE the programmatic
+//                        dependency on the previous launch resolves (griddepcontrol.wait);
+//                        only the stores wait.  Legal when the previous launch on the
+//                        stream does not write A or B (the launch loop, a1: the previous
+//                        launch is the same add, which writes only C) -- it overlaps this
+//                        launch's DRAM ramp with the previous launch's tail.
 //   K2  vadd_tma         persistent CTAs; one producer lane issues 1-D cp.async.bulk
 //                        copies of an A tile and a B tile into a `stages`-deep smem ring
 //                        (mbarrier complete_tx); consumer warps add from smem and either
@@ -113,10 +122,42 @@ __device__ __forceinline__ void add_edges(const float* A, const float* B, float*
 // so each warp-level access is one contiguous 512 B (VW=4) or 1 KiB (VW=8) run.  All
 // 2*UNROLL loads are issued before the first add: that is the memory-level parallelism.
 template <int VW, int UNROLL, int LD, int ST>
+__device__ __forceinline__ void vec_tile(const float* a, const float* b, float* c, size_t tile, size_t tile_vecs,
+                                         size_t nvec, uint64_t pol, bool& waited)
+{
+    using V = typename vec_t<VW>::type;
+    const size_t v0 = tile * tile_vecs + threadIdx.x;
+    if ((tile + 1) * tile_vecs <= nvec) {
+        V ra[UNROLL], rb[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j)
+            ra[j] = ldg_vec<VW, LD>(a + (v0 + static_cast<size_t>(j) * blockDim.x) * VW, pol);
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j)
+            rb[j] = ldg_vec<VW, LD>(b + (v0 + static_cast<size_t>(j) * blockDim.x) * VW, pol);
+        if (!waited) { pdl_wait(); waited = true; }      // EARLY: only the stores wait for the previous launch
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j)
+            stg_vec<VW, ST>(c + (v0 + static_cast<size_t>(j) * blockDim.x) * VW,
+                            add_vec(ra[j], rb[j]), pol);
+    } else {
+        if (!waited) { pdl_wait(); waited = true; }
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) {
+            const size_t v = v0 + static_cast<size_t>(j) * blockDim.x;
+            if (v < nvec) {
+                const V x = ldg_vec<VW, LD>(a + v * VW, pol);
+                const V y = ldg_vec<VW, LD>(b + v * VW, pol);
+                stg_vec<VW, ST>(c + v * VW, add_vec(x, y), pol);
+            }
+        }
+    }
+}
+
+template <int VW, int UNROLL, int LD, int ST, bool EARLY>
 __global__ void vadd_vec(const float* A, const float* B, float* C, size_t n, size_t head,
                          size_t nvec, size_t ntiles)
 {
-    using V = typename vec_t<VW>::type;
     uint64_t pol = 0;
     if constexpr (LD == LD_NA_EF || ST == ST_NA_EF) pol = l2_evict_first_policy();
 
@@ -125,35 +166,68 @@ __global__ void vadd_vec(const float* A, const float* B, float* C, size_t n, siz
     float* c = C + head;
     const size_t tile_vecs = static_cast<size_t>(blockDim.x) * UNROLL;
     pdl_launch_dependents();
-    pdl_wait();   // everything above overlapped the previous launch's tail
+    bool waited = !EARLY;
+    if constexpr (!EARLY) pdl_wait();   // everything above overlapped the previous launch's tail
 
-    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t v0 = tile * tile_vecs + threadIdx.x;
-        if ((tile + 1) * tile_vecs <= nvec) {
-            V ra[UNROLL], rb[UNROLL];
-#pragma unroll
-            for (int j = 0; j < UNROLL; ++j)
-                ra[j] = ldg_vec<VW, LD>(a + (v0 + static_cast<size_t>(j) * blockDim.x) * VW, pol);
-#pragma unroll
-            for (int j = 0; j < UNROLL; ++j)
-                rb[j] = ldg_vec<VW, LD>(b + (v0 + static_cast<size_t>(j) * blockDim.x) * VW, pol);
-#pragma unroll
-            for (int j = 0; j < UNROLL; ++j)
-                stg_vec<VW, ST>(c + (v0 + static_cast<size_t>(j) * blockDim.x) * VW,
-                                add_vec(ra[j], rb[j]), pol);
-        } else {
-#pragma unroll
-            for (int j = 0; j < UNROLL; ++j) {
-                const size_t v = v0 + static_cast<size_t>(j) * blockDim.x;
-                if (v < nvec) {
-                    const V x = ldg_vec<VW, LD>(a + v * VW, pol);
-                    const V y = ldg_vec<VW, LD>(b + v * VW, pol);
-                    stg_vec<VW, ST>(c + v * VW, add_vec(x, y), pol);
-                }
-            }
-        }
-    }
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        vec_tile<VW, UNROLL, LD, ST>(a, b, c, tile, tile_vecs, nvec, pol, waited);
+    if (!waited) pdl_wait();
     if (blockIdx.x == 0) add_edges(A, B, C, n, head, head + nvec * VW, threadIdx.x);
+}
+
+// ------------------------------------------------------------------------------ K1c
+// The vec tile body under the cluster-launch-control scheduler.  Grid = one CTA per tile;
+// a running CTA, before it touches its tile, asks the hardware to cancel one CTA that has
+// not started yet (try_cancel, answered through the async proxy into shared memory and
+// counted on an mbarrier) and -- after its own tile -- processes the cancelled CTA's tile
+// instead of exiting.  The request's latency hides behind the tile's loads.  One response
+// slot: every thread reads it, the CTA barrier orders those reads before thread 0 re-arms it.
+template <int VW, int UNROLL, int LD, int ST, bool EARLY>
+__global__ void vadd_vec_clc(const float* A, const float* B, float* C, size_t n, size_t head,
+                             size_t nvec, size_t ntiles)
+{
+    __shared__ __align__(16) unsigned char resp[16];
+    __shared__ __align__(8) unsigned long long bar_storage;
+    const uint32_t resp_s = smem_u32(resp), bar = smem_u32(&bar_storage);
+    uint64_t pol = 0;
+    if constexpr (LD == LD_NA_EF || ST == ST_NA_EF) pol = l2_evict_first_policy();
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1u);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+
+    const float* a = A + head;
+    const float* b = B + head;
+    float* c = C + head;
+    const size_t tile_vecs = static_cast<size_t>(blockDim.x) * UNROLL;
+    pdl_launch_dependents();
+    bool waited = !EARLY;
+    if constexpr (!EARLY) pdl_wait();
+
+    uint32_t tile = blockIdx.x, ph = 0;
+    while (true) {
+        if (threadIdx.x == 0) {                           // ask for the tile after this one
+            fence_proxy_async_smem();
+            mbar_arrive_expect_tx(bar, 16u);
+            clc_try_cancel(resp_s, bar);
+        }
+        if (tile < ntiles) vec_tile<VW, UNROLL, LD, ST>(a, b, c, tile, tile_vecs, nvec, pol, waited);
+        if (tile == 0) {                                  // edges travel with tile 0, whoever runs it
+            if (!waited) { pdl_wait(); waited = true; }
+            add_edges(A, B, C, n, head, head + nvec * VW, threadIdx.x);
+        }
+        mbar_wait(bar, ph);
+        ph ^= 1u;
+        uint32_t next = 0;
+        const bool ok = clc_query(resp_s, next);
+        __syncthreads();                                  // all reads of the slot precede its re-arm
+        if (!ok) break;
+        tile = next;
+    }
+    if (!waited) pdl_wait();
 }
 
 // ------------------------------------------------------------------------------ K2
@@ -368,6 +442,7 @@ vadd_tma_clc(const float* A, const float* B, float* C, size_t n, size_t head, si
                         tile = next;
                         have_next = true;
                         if (!failed) {
+                            fence_proxy_async_smem();             // the generic-proxy read of the slot precedes its async re-write
                             mbar_arrive_expect_tx(clc_bar(j), 16u);
                             clc_try_cancel(clc_resp(j), clc_bar(j));
                             ++outstanding;
@@ -414,12 +489,16 @@ vadd_tma_clc(const float* A, const float* B, float* C, size_t n, size_t head, si
             }
             for (; v < nv; v += n_cons)
                 stg128<ST>(cg + v * 4u, add_vec(lds128(sa + v * 16u), lds128(sb + v * 16u)), pol);
+            // the scalar head/tail travel with tile 0, whichever CTA ends up running it (CTA 0 may be
+            // cancelled and its tile taken over under cluster launch control)
+            if (tile == 0) add_edges(A, B, C, n, head, head + nvec4 * 4u, ct);
 
             __syncwarp();
             if ((threadIdx.x & 31u) == 0) mbar_arrive(empty_bar(s));
             if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        if (blockIdx.x == 0) add_edges(A, B, C, n, head, head + nvec4 * 4u, ct);
+        // no vector body at all (n < 4 after the head): the grid is the single CTA 0
+        if (body_bytes == 0 && blockIdx.x == 0) add_edges(A, B, C, n, head, head + nvec4 * 4u, ct);
     }
 }
 

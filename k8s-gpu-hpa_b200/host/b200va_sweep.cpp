@@ -6,7 +6,11 @@
 //          flagged "l2_resident": true -- NOT an HBM figure)
 //   cold   rotating through enough buffer sets that the footprint is >= 4x L2, so every
 //          launch streams from HBM
-//   graph  hot buffers, launches captured 100 per CUDA graph (launch latency amortised)
+//   cold_chain  the cold rotation launched with B200VA_F_INPUTS_STABLE (consecutive launches never
+//          write each other's inputs): loads run ahead of the programmatic dependency, so the
+//          next launch's DRAM ramp overlaps the previous launch's tail
+//   graph  hot buffers, launches captured 100 per CUDA graph (launch latency amortised; launches
+//          2..100 of a graph run with early loads -- the loop API knows its own predecessor)
 // plus the reference-shape control K0 (hot).  Times are CUDA-event batch times / launches.
 //
 //     b200va_sweep [--lo 16] [--hi 30] [--kernel auto|k0|k1|k2|k3]
@@ -103,6 +107,7 @@ int main(int argc, char** argv)
         const double hot = time_batches([&] { for (int i = 0; i < iters; ++i) VA(b200va_add_f32(A(0), B(0), C(0), n, variant, st)); });
         const double cold = sets > 1 ? time_batches([&] { for (int i = 0; i < iters; ++i) { const int s = i % sets; VA(b200va_add_f32(A(s), B(s), C(s), n, variant, st)); } })
                                      : hot;
+        const double cold_chain = time_batches([&] { for (int i = 0; i < iters; ++i) { const int s = sets > 1 ? i % sets : 0; VA(b200va_add_f32_ex(A(s), B(s), C(s), n, variant, B200VA_F_INPUTS_STABLE, st)); } });
         b200va_loop_t* loop = nullptr;
         VA(b200va_loop_create(&loop, A(0), B(0), C(0), n, variant, 100));
         const double graph = time_batches([&] { VA(b200va_loop_run(loop, iters, st)); });
@@ -121,12 +126,12 @@ int main(int argc, char** argv)
         auto gbps = [&](double us) { return 12.0 * static_cast<double>(n) / us / 1e3; };
         std::printf("{\"log2_n\": %d, \"n\": %zu, \"algorithmic_bytes\": %zu, \"l2_resident\": %s, \"buffer_sets\": %d, "
                     "\"launches_per_sample\": %d, \"kind\": %d, \"threads\": %d, \"unroll\": %d, \"mismatches\": %llu, "
-                    "\"us_hot\": %.3f, \"us_cold\": %.3f, \"us_graph\": %.3f, \"us_k0\": %.3f, "
-                    "\"GBps_hot\": %.1f, \"GBps_cold\": %.1f, \"GBps_graph\": %.1f, \"GBps_k0\": %.1f, "
+                    "\"us_hot\": %.3f, \"us_cold\": %.3f, \"us_cold_chain\": %.3f, \"us_graph\": %.3f, \"us_k0\": %.3f, "
+                    "\"GBps_hot\": %.1f, \"GBps_cold\": %.1f, \"GBps_cold_chain\": %.1f, \"GBps_graph\": %.1f, \"GBps_k0\": %.1f, "
                     "\"elems_per_s_cold\": %.4e, \"elems_per_s_graph\": %.4e}\n",
                     k, n, set_bytes, set_bytes <= static_cast<size_t>(di.l2_bytes) ? "true" : "false", sets, iters, t.kind,
-                    t.threads, t.unroll, static_cast<unsigned long long>(h[0]), hot, cold, graph, k0, gbps(hot), gbps(cold),
-                    gbps(graph), gbps(k0), static_cast<double>(n) / (cold * 1e-6), static_cast<double>(n) / (graph * 1e-6));
+                    t.threads, t.unroll, static_cast<unsigned long long>(h[0]), hot, cold, cold_chain, graph, k0, gbps(hot), gbps(cold),
+                    gbps(cold_chain), gbps(graph), gbps(k0), static_cast<double>(n) / (cold * 1e-6), static_cast<double>(n) / (graph * 1e-6));
         std::fflush(stdout);
         CK(cudaFree(pool));
     }

@@ -24,7 +24,10 @@
 //   --hpa-threshold T  utilisation the HPA compares with (default 5, cuda-test-hpa.yaml:21)
 //   --cpu-baseline   also time a host-threads C[i]=A[i]+B[i] loop (reported, never used)
 //   --json PATH      write the result line to PATH as well as stdout
-//   --metrics-file P rewrite P every 0.5 s with `dcgm_gpu_utilization{...} <NVML util>` (Prometheus text)
+//   --metrics-file P rewrite P every 0.5 s with `dcgm_gpu_utilization{...} <NVML util>` (Prometheus text;
+//                    the namespace label comes from $POD_NAMESPACE, default "default")
+//   --host-mem pinned|pageable   staged mode: library-allocated pinned arrays (default) or plain malloc,
+//                    what the reference process has; the stager page-locks those once and reuses them
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <sched.h>
@@ -86,7 +89,8 @@ struct Options {
     bool cpu_baseline = false;
     int cpu_threads = 0;
     uint64_t seed = 0x0A;        // ctr generator: A uses seed, B uses seed + 1 (defaults 0x0A / 0x0B)
-    int stage_mode = 2;          // staged mode pipeline: 2 lanes (default), 0 slot streams, 1 zero-copy
+    int stage_mode = B200VA_STAGE_AUTO;   // staged mode pipeline: auto (lanes / register-once), 0 slot streams, 1 zero-copy
+    bool pageable = false;       // staged mode: host arrays from plain malloc instead of b200va_host_alloc
     std::string json_path;
     std::string metrics_file;    // Prometheus text snapshot of the NVML utilisation (GPU 0), rewritten every 0.5 s
     bool any = false;
@@ -170,8 +174,14 @@ Options parse(int argc, char** argv)
         else if (a == "--hpa-threshold") o.hpa_threshold = std::atof(need(i));
         else if (a == "--cpu-baseline") o.cpu_baseline = true;
         else if (a == "--cpu-threads") o.cpu_threads = std::atoi(need(i));
-        else if (a == "--zero-copy") o.stage_mode = 1;
-        else if (a == "--slot-streams") o.stage_mode = 0;
+        else if (a == "--zero-copy") o.stage_mode = B200VA_STAGE_ZEROCOPY;
+        else if (a == "--slot-streams") o.stage_mode = B200VA_STAGE_SLOTS;
+        else if (a == "--bounce") o.stage_mode = B200VA_STAGE_BOUNCE;
+        else if (a == "--host-mem") {
+            const std::string v = need(i);
+            if (v != "pinned" && v != "pageable") { std::fprintf(stderr, "bad --host-mem (pinned|pageable)\n"); std::exit(EXIT_FAILURE); }
+            o.pageable = v == "pageable";
+        }
         else if (a == "--json") o.json_path = need(i);
         else if (a == "--metrics-file") { o.metrics_file = need(i); o.nvml = true; }
         else if (a == "--help" || a == "-h") {
@@ -179,7 +189,7 @@ Options parse(int argc, char** argv)
                         "                 [--mode sample|resident|staged] [--gen rand|ctr] [--seed S] [--graph B]\n"
                         "                 [--verify full|none] [--duration S] [--target-util P] [--period-ms M]\n"
                         "                 [--nvml] [--hpa-threshold T] [--cpu-baseline] [--cpu-threads T]\n"
-                        "                 [--zero-copy] [--json PATH] [--metrics-file PATH]\n"
+                        "                 [--zero-copy] [--host-mem pinned|pageable] [--json PATH] [--metrics-file PATH]\n"
                         "no arguments: the reference image's behaviour (50000 elements, one add, verify).\n");
             std::exit(0);
         } else {
@@ -293,12 +303,13 @@ struct Nvml {
     void write_metrics(const std::string& path, size_t i, int util_pct) const
     {
         const char* pod = std::getenv("HOSTNAME");
+        const char* ns = std::getenv("POD_NAMESPACE");       // downward-API convention; the reference deploys into "default"
         const std::string tmp = path + ".tmp";
         if (FILE* f = std::fopen(tmp.c_str(), "w")) {
             std::fprintf(f, "# HELP dcgm_gpu_utilization GPU utilization (in %%), NVML utilization.gpu as sampled by vectorAdd.\n"
                             "# TYPE dcgm_gpu_utilization gauge\n"
-                            "dcgm_gpu_utilization{gpu=\"%zu\",uuid=\"%s\",pod=\"%s\",namespace=\"default\"} %d\n",
-                         i, i < uuid.size() ? uuid[i].c_str() : "unknown", pod ? pod : "", util_pct);
+                            "dcgm_gpu_utilization{gpu=\"%zu\",uuid=\"%s\",pod=\"%s\",namespace=\"%s\"} %d\n",
+                         i, i < uuid.size() ? uuid[i].c_str() : "unknown", pod ? pod : "", (ns && *ns) ? ns : "default", util_pct);
             std::fclose(f);
             std::rename(tmp.c_str(), path.c_str());
         }
@@ -362,8 +373,10 @@ int run_sample(const Options& o)
             std::fprintf(stderr, "Result verification failed at element %zu!\n", bad);
             return EXIT_FAILURE;
         }
+        std::printf("Test PASSED\n");
+    } else {
+        std::printf("Test SKIPPED (--verify none)\n");   // never claim a pass that was not checked
     }
-    std::printf("Test PASSED\n");
 
     ck(cudaStreamDestroy(st), "destroy stream");
     ck(cudaFree(d_A), "free device vector A");
@@ -395,6 +408,8 @@ struct ShardResult {
     long long launches = 0;
     uint64_t mismatches = 0, first_bad = ~0ull, digest[2] = {0, 0};
     std::vector<int> util_samples;
+    double first_pass_wall_ms = 0;   // staged: wall clock of the first pass (register-once pays its pinning here)
+    int stage_mode = -2;             // staged: the pipeline the stager resolved to
     std::string error;
 };
 
@@ -421,7 +436,13 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "create stream");
         CK(cudaEventCreate(&e0), "create event"); CK(cudaEventCreate(&e1), "create event");
         CK(cudaMalloc(&dRes, 4 * sizeof(uint64_t)), "allocate result words");
-        if (staged) {
+        if (staged && o.pageable) {
+            // the reference process's own memory: plain malloc (a2); the stager page-locks it on first sight
+            hA = static_cast<float*>(std::malloc(m ? m * 4 : 4));
+            hB = static_cast<float*>(std::malloc(m ? m * 4 : 4));
+            hC = static_cast<float*>(std::malloc(m ? m * 4 : 4));
+            if (!hA || !hB || !hC) { fail("allocate host vectors", "out of memory"); ok = false; }
+        } else if (staged) {
             VA(b200va_host_alloc(reinterpret_cast<void**>(&hA), m * 4), "allocate pinned A");
             VA(b200va_host_alloc(reinterpret_cast<void**>(&hB), m * 4), "allocate pinned B");
             VA(b200va_host_alloc(reinterpret_cast<void**>(&hC), m * 4), "allocate pinned C");
@@ -448,10 +469,13 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
         const double before = r.gpu_ms;
         if (staged) {
             for (int i = 0; i < count && ok; ++i) {
+                const auto w0 = clk::now();
                 VA(b200va_stager_add_f32(stager, hA, hB, hC, m, o.variant, o.stage_mode), "staged add");
                 float ms = 0; if (ok) b200va_stager_last_ms(stager, &ms);
+                if (r.launches + i == 0) r.first_pass_wall_ms = secs_since(w0) * 1e3;   // includes one-off page-locking
                 r.gpu_ms += ms;
             }
+            if (ok) b200va_stager_last_mode(stager, &r.stage_mode);
         } else {
             CK(cudaEventRecord(e0, st), "record event");
             VA(b200va_loop_run(loop, count, st), "launch vectorAdd kernel");
@@ -522,8 +546,9 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
     }
     if (st) cudaStreamSynchronize(st);
     if (loop) b200va_loop_destroy(loop);
-    if (stager) b200va_stager_destroy(stager);
-    b200va_host_free(hA); b200va_host_free(hB); b200va_host_free(hC);
+    if (stager) b200va_stager_destroy(stager);    // unregisters the malloc'd arrays before they are freed
+    if (staged && o.pageable) { std::free(hA); std::free(hB); std::free(hC); }
+    else { b200va_host_free(hA); b200va_host_free(hB); b200va_host_free(hC); }
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dRes);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
@@ -595,13 +620,21 @@ int run_sharded(const Options& o)
                   launches ? max_ms / static_cast<double>(launches) : 0.0, eps, gbps, gbps / (8000.0 * o.gpus), max_wall,
                   max_wall > 0 ? max_ms * 1e-3 / max_wall : 0.0, mism, dig[0], dig[1]);
     js = buf;
+    if (o.mode == "staged") {
+        std::snprintf(buf, sizeof buf, ", \"host_mem\": \"%s\", \"stage_mode\": %d, \"first_pass_wall_ms\": %.3f",
+                      o.pageable ? "pageable (malloc)" : "pinned (b200va_host_alloc)", res[0].stage_mode, res[0].first_pass_wall_ms);
+        js += buf;
+    }
     if (have_nvml) {
         double sum = 0; int cnt = 0, mx = 0;
         for (auto& r : res) for (int u : r.util_samples) if (u >= 0) { sum += u; ++cnt; mx = std::max(mx, u); }
         const double mean = cnt ? sum / cnt : 0.0;
         std::snprintf(buf, sizeof buf, ", \"nvml_util_mean\": %.1f, \"nvml_util_max\": %d, \"nvml_samples\": %d, "
-                      "\"hpa_threshold\": %.1f, \"hpa_would_scale\": %s, \"nvml_sample_period_s\": 0.5, \"nvml_trace\": [",
-                      mean, mx, cnt, o.hpa_threshold, mean > o.hpa_threshold ? "true" : "false");
+                      "\"hpa_threshold\": %.1f, \"hpa_tolerance\": 0.1, \"hpa_ratio\": %.4f, \"hpa_would_scale\": %s, "
+                      "\"nvml_sample_period_s\": 0.5, \"nvml_trace\": [",
+                      mean, mx, cnt, o.hpa_threshold, o.hpa_threshold > 0 ? mean / o.hpa_threshold : 0.0,
+                      // the controller acts only outside its 10 % tolerance band (hpa_replay.hpa_desired_replicas)
+                      mean > o.hpa_threshold * 1.1 ? "true" : "false");
         js += buf;
         for (size_t g = 0; g < res.size(); ++g) {          // one utilisation trace per GPU (0.5 s apart)
             js += g ? ", [" : "[";

@@ -28,6 +28,8 @@ DCGM_INTERVAL_S = 10.0      # dcgm-exporter.yaml:37   (-c 10000)
 SCRAPE_INTERVAL_S = 1.0     # kube-prometheus-stack-values.yaml:5
 HPA_SYNC_S = 15.0           # kube-controller-manager default --horizontal-pod-autoscaler-sync-period
 HPA_TOLERANCE = 0.1         # kube-controller-manager default
+HPA_DOWNSCALE_STABILIZATION_S = 300.0   # kube-controller-manager default --horizontal-pod-autoscaler-downscale-stabilization:
+                                        # the controller scales down only to the HIGHEST recommendation of the last 5 minutes
 
 
 @dataclass(frozen=True)
@@ -72,6 +74,7 @@ class Replay:
     scrape_interval_s: float = SCRAPE_INTERVAL_S
     hpa_sync_s: float = HPA_SYNC_S
     target: float = HPA_TARGET
+    downscale_stabilization_s: float = HPA_DOWNSCALE_STABILIZATION_S
     events: list[tuple[float, float | None, int]] = field(default_factory=list)
 
     def run(self, traces: dict[str, list[tuple[float, float]]], duration_s: float, replicas: int = 1) -> list[tuple[float, float | None, int]]:
@@ -82,6 +85,7 @@ class Replay:
         exported: dict[str, float] = {}              # what the exporter currently serves
         self.events = []
         t, next_dcgm, next_hpa, metric = 0.0, 0.0, self.hpa_sync_s, None
+        recommendations: list[tuple[float, int]] = []        # (time, desired replicas) of past syncs
         while t <= duration_s + 1e-9:
             if t + 1e-9 >= next_dcgm:                # exporter refreshes its gauges
                 for p in pods[:replicas]:
@@ -92,7 +96,13 @@ class Replay:
             live = [Sample("node0", p, "default", exported[p]) for p in pods[:replicas] if p in exported]
             metric = cuda_test_gpu_avg(live, {p: "cuda-test" for p in pods})   # rule evaluated on each scrape
             if t + 1e-9 >= next_hpa:
-                replicas = hpa_desired_replicas(replicas, metric, self.target)
+                desired = hpa_desired_replicas(replicas, metric, self.target)
+                recommendations.append((t, desired))
+                # scale-ups apply at once; a scale-down is held to the highest recommendation
+                # inside the stabilization window (the controller's default behaviour; the reference only
+                # says "if the usage drops low enough, a scaledown will occur", README.md:121)
+                recent = [d for (ts, d) in recommendations if ts >= t - self.downscale_stabilization_s - 1e-9]
+                replicas = min(replicas, max(recent)) if desired < replicas else desired
                 replicas = min(replicas, len(pods))
                 self.events.append((t, metric, replicas))
                 next_hpa += self.hpa_sync_s

@@ -45,8 +45,13 @@ def _stream_ptr(stream) -> int:
     return stream.cuda_stream
 
 
-def add(a, b, out=None, *, variant=K_AUTO, tune: Tune | None = None, stream=None):
-    """C = A + B on the current CUDA stream (asynchronous). ``out`` may be ``a`` or ``b``."""
+def add(a, b, out=None, *, variant=K_AUTO, tune: Tune | None = None, stream=None, inputs_stable: bool = False,
+        full_matrix: bool = False):
+    """C = A + B on the current CUDA stream (asynchronous). ``out`` may be ``a`` or ``b``.
+    ``inputs_stable``: b200va_add_f32_ex with B200VA_F_INPUTS_STABLE (the previous launch on the
+    stream does not write a or b).  ``full_matrix``: send an explicit ``tune`` to
+    libb200va_tune.so, which carries every geometry (the production library refuses the
+    ones AUTO never picks with ERR_VARIANT)."""
     torch = _torch()
     if a.numel() != b.numel():
         raise ValueError("a and b differ in length")
@@ -57,7 +62,11 @@ def add(a, b, out=None, *, variant=K_AUTO, tune: Tune | None = None, stream=None
     pa, pb, pc = _dev_ptr(a, "a"), _dev_ptr(b, "b"), _dev_ptr(out, "out")
     with torch.cuda.device(a.device):
         if tune is not None:
-            check(lib.b200va_add_f32_tuned(pa, pb, pc, a.numel(), C.byref(tune), _stream_ptr(stream)), "b200va_add_f32_tuned")
+            h = capi.tune_lib() if full_matrix else lib
+            check(h.b200va_add_f32_tuned(pa, pb, pc, a.numel(), C.byref(tune), _stream_ptr(stream)), "b200va_add_f32_tuned")
+        elif inputs_stable:
+            check(lib.b200va_add_f32_ex(pa, pb, pc, a.numel(), _variant(variant), capi.F_INPUTS_STABLE, _stream_ptr(stream)),
+                  "b200va_add_f32_ex")
         else:
             check(lib.b200va_add_f32(pa, pb, pc, a.numel(), _variant(variant), _stream_ptr(stream)), "b200va_add_f32")
     return out
@@ -71,6 +80,38 @@ def add_loop(a, b, out, iters: int, *, graph_batch: int = 0, variant=K_AUTO, str
         check(lib.b200va_add_f32_loop(pa, pb, pc, a.numel(), _variant(variant), iters, graph_batch,
                                       _stream_ptr(stream)), "b200va_add_f32_loop")
     return out
+
+
+class Loop:
+    """The persistent launch loop (a1): ``graph_batch`` launches captured once into a CUDA graph,
+    ``run(iters)`` replays it asynchronously on the current stream (b200va_loop_*)."""
+
+    def __init__(self, a, b, out, *, graph_batch: int = 50, variant=K_AUTO):
+        torch = _torch()
+        self._h = C.c_void_p()
+        self._keep = (a, b, out)
+        self._device = a.device
+        with torch.cuda.device(a.device):
+            check(lib.b200va_loop_create(C.byref(self._h), _dev_ptr(a, "a"), _dev_ptr(b, "b"), _dev_ptr(out, "out"), a.numel(),
+                                         _variant(variant), graph_batch), "b200va_loop_create")
+
+    def run(self, iters: int, *, stream=None) -> None:
+        torch = _torch()
+        with torch.cuda.device(self._device):
+            check(lib.b200va_loop_run(self._h, iters, _stream_ptr(stream)), "b200va_loop_run")
+
+    def close(self) -> None:
+        """Destroy the graph; the stream must have drained."""
+        if self._h:
+            lib.b200va_loop_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        _torch().cuda.synchronize(self._device)
+        self.close()
 
 
 _TORCH_DT = {"f32": "float32", "f64": "float64", "f16": "float16", "bf16": "bfloat16"}
@@ -198,15 +239,27 @@ class Stager:
 
     def add(self, a, b, out, *, variant=K_AUTO, zero_copy: bool = False, mode: int | None = None) -> float:
         """Synchronous; returns the device-timed milliseconds of the whole pipeline.
-        mode: 0 slot streams, 1 zero-copy kernel, 2 lanes (one stream per direction)."""
+        mode: -1 auto (default), 0 slot streams, 1 zero-copy kernel, 2 lanes (one stream per
+        direction), 3 pageable arrays through a pinned bounce ring, 4 register-once."""
         n = a.size if isinstance(a, np.ndarray) else a.numel()
         if mode is None:
-            mode = 1 if zero_copy else 0
+            mode = capi.STAGE_ZEROCOPY if zero_copy else capi.STAGE_AUTO
         check(lib.b200va_stager_add_f32(self._h, _host_ptr(a, "a"), _host_ptr(b, "b"), _host_ptr(out, "out"), n,
                                         _variant(variant), mode), "b200va_stager_add_f32")
         ms = C.c_float()
         check(lib.b200va_stager_last_ms(self._h, C.byref(ms)), "b200va_stager_last_ms")
         return ms.value
+
+    @property
+    def last_mode(self) -> int:
+        """The pipeline the last ``add`` actually ran (after AUTO / fallbacks)."""
+        m = C.c_int(-2)
+        check(lib.b200va_stager_last_mode(self._h, C.byref(m)), "b200va_stager_last_mode")
+        return m.value
+
+    def release_host(self) -> None:
+        """Unregister the host arrays the register-once path page-locked."""
+        check(lib.b200va_stager_release_host(self._h), "b200va_stager_release_host")
 
     def close(self):
         if self._h:

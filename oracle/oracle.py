@@ -39,6 +39,9 @@ for _n, _r, _a in [
     ("oracle_fill_ctr_pair_mt", None, [_P, _P, _P, _SZ, _U64, _U64, _U64, _I]),
     ("oracle_vadd_digest_f32_mt", None, [_P, _P, _SZ, _I, _P]),
     ("oracle_time_vadd_mt", _I, [_SZ, _I, _I, _I, _P]),
+    ("oracle_time_vadd_mt_ex", _I, [_SZ, _I, _I, _I, _I, _P]),
+    ("oracle_vadd_f32_mt_nt", None, [_P, _P, _P, _SZ, _I]),
+    ("oracle_nt_width", _I, []),
     ("oracle_stream", _I, [_I, _I, _P, _P, _P, _SZ, C.c_double]),
     ("oracle_half_to_float", None, [_P, _P, _SZ]),
     ("oracle_float_to_half", None, [_P, _P, _SZ]),
@@ -67,6 +70,18 @@ def vadd_mt(a: np.ndarray, b: np.ndarray, threads: int = 0) -> np.ndarray:
     c = np.empty_like(_f32(a))
     _lib.oracle_vadd_f32_mt(a.ctypes.data, _f32(b).ctypes.data, c.ctypes.data, a.size, threads or num_cpus())
     return c
+
+
+def vadd_mt_nt(a: np.ndarray, b: np.ndarray, threads: int = 0) -> np.ndarray:
+    """The non-temporal-store timing variant (SSE/AVX/AVX-512 vaddps + movntps): same bits as vadd."""
+    c = np.empty_like(_f32(a))
+    _lib.oracle_vadd_f32_mt_nt(a.ctypes.data, _f32(b).ctypes.data, c.ctypes.data, a.size, threads or num_cpus())
+    return c
+
+
+def nt_width() -> int:
+    """Vector width (bits) of the non-temporal variant on this host: 512, 256, 128 (0: not x86-64)."""
+    return int(_lib.oracle_nt_width())
 
 
 def softfloat_vadd_bits(ua: np.ndarray, ub: np.ndarray) -> np.ndarray:
@@ -150,7 +165,7 @@ def cpu_quota() -> float:
     return float(_lib.oracle_cpu_quota())
 
 
-def best_thread_count(n: int = 1 << 26) -> tuple[int, dict[int, float]]:
+def best_thread_count(n: int = 1 << 26, nt_stores: bool = False) -> tuple[int, dict[int, float]]:
     """All the host threads the add can USE: tries the affinity count, multiples of the cgroup
     quota and a few fixed counts on a short sample (median of 3 passes each) and returns the
     fastest (threads, {threads: elem/s})."""
@@ -160,18 +175,32 @@ def best_thread_count(n: int = 1 << 26) -> tuple[int, dict[int, float]]:
         cands |= {max(1, min(ncpu, int(round(k * quota)))) for k in (1, 1.5, 2, 3, 4)}
     rates = {}
     for t in sorted(cands):
-        secs = sorted(time_vadd_mt(n, t, 1, 3))
+        secs = sorted(time_vadd_mt(n, t, 1, 3, nt_stores))
         rates[t] = n / secs[1]
     return max(rates, key=rates.get), rates
 
 
-def time_vadd_mt(n: int, threads: int = 0, warmup: int = 1, reps: int = 5) -> list[float]:
-    """Per-pass seconds of the all-cores add over n elements (buffers first-touched by the workers)."""
+def time_vadd_mt(n: int, threads: int = 0, warmup: int = 1, reps: int = 5, nt_stores: bool = False) -> list[float]:
+    """Per-pass seconds of the all-cores add over n elements (buffers first-touched by the workers).
+    nt_stores: non-temporal stores (no write-allocate read of C) instead of regular ones."""
     secs = (C.c_double * reps)()
-    rc = _lib.oracle_time_vadd_mt(n, threads or num_cpus(), warmup, reps, secs)
+    rc = _lib.oracle_time_vadd_mt_ex(n, threads or num_cpus(), warmup, reps, 1 if nt_stores else 0, secs)
     if rc != 0:
         raise MemoryError("oracle_time_vadd_mt: allocation failed")
     return list(secs)
+
+
+def best_cpu_config(n: int = 1 << 26) -> dict:
+    """The fastest way this host adds two vectors: regular vs non-temporal stores, each at its
+    best thread count.  {"stores", "threads", "rate", "tried": {...}}"""
+    out = {"tried": {}}
+    for nt in (False, True):
+        t, rates = best_thread_count(n, nt)
+        name = f"non-temporal ({nt_width()}-bit vmovntps)" if nt else "regular (write-allocate)"
+        out["tried"][name] = {"threads": t, "elements_per_s": rates[t], "all": {str(k): v for k, v in sorted(rates.items())}}
+        if "rate" not in out or rates[t] > out["rate"]:
+            out.update(stores=name, threads=t, rate=rates[t], nt=nt)
+    return out
 
 
 # ---------------------------------------------------------------- f4: STREAM-style ops

@@ -40,6 +40,9 @@
 #include <string.h>
 #include <time.h>
 #include <unistd.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 /* ------------------------------------------------------------------ a4: the add */
 
@@ -252,7 +255,7 @@ double oracle_cpu_quota(void)
 
 typedef struct {
     const float *a, *b; float *c; size_t lo, hi;
-    uint64_t seed_a, seed_b, first; int op;                /* 0 add, 1 fill, 2 digest */
+    uint64_t seed_a, seed_b, first; int op;                /* 0 add, 1 fill, 2 digest, 3 add with non-temporal stores */
     uint64_t dig[2];
 } span_t;
 
@@ -263,11 +266,74 @@ static void add_span(const float *a, const float *b, float *c, size_t lo, size_t
         c[i] = a[i] + b[i];
 }
 
+/* Non-temporal-store variants of the same add, for the reported CPU baseline only: a
+ * regular store to a line that is not in cache first READS it (write-allocate), so the
+ * scalar/AVX2 loop above moves ~16 B per element through DRAM, not 12.  Streaming stores
+ * (movntps / vmovntps) skip that read.  vaddps is the same correctly-rounded IEEE add per
+ * lane as addss, so the results are bit-identical (checked in tests/test_oracle.py).
+ * The widest ISA the host supports is picked at run time. */
+#if defined(__x86_64__)
+__attribute__((target("avx512f")))
+static void add_span_nt512(const float *a, const float *b, float *c, size_t lo, size_t hi)
+{
+    size_t i = lo;
+    for (; i < hi && ((uintptr_t)(c + i) & 63u); ++i) c[i] = a[i] + b[i];
+    for (; i + 16 <= hi; i += 16)
+        _mm512_stream_ps(c + i, _mm512_add_ps(_mm512_loadu_ps(a + i), _mm512_loadu_ps(b + i)));
+    for (; i < hi; ++i) c[i] = a[i] + b[i];
+    _mm_sfence();
+}
+
+__attribute__((target("avx")))
+static void add_span_nt256(const float *a, const float *b, float *c, size_t lo, size_t hi)
+{
+    size_t i = lo;
+    for (; i < hi && ((uintptr_t)(c + i) & 31u); ++i) c[i] = a[i] + b[i];
+    for (; i + 8 <= hi; i += 8)
+        _mm256_stream_ps(c + i, _mm256_add_ps(_mm256_loadu_ps(a + i), _mm256_loadu_ps(b + i)));
+    for (; i < hi; ++i) c[i] = a[i] + b[i];
+    _mm_sfence();
+}
+
+static void add_span_nt128(const float *a, const float *b, float *c, size_t lo, size_t hi)
+{
+    size_t i = lo;
+    for (; i < hi && ((uintptr_t)(c + i) & 15u); ++i) c[i] = a[i] + b[i];
+    for (; i + 4 <= hi; i += 4)
+        _mm_stream_ps(c + i, _mm_add_ps(_mm_loadu_ps(a + i), _mm_loadu_ps(b + i)));
+    for (; i < hi; ++i) c[i] = a[i] + b[i];
+    _mm_sfence();
+}
+
+/* 512 / 256 / 128: the vector width the non-temporal variant uses on this host. */
+int oracle_nt_width(void)
+{
+    __builtin_cpu_init();
+    if (__builtin_cpu_supports("avx512f")) return 512;
+    if (__builtin_cpu_supports("avx")) return 256;
+    return 128;
+}
+
+static void add_span_nt(const float *a, const float *b, float *c, size_t lo, size_t hi)
+{
+    switch (oracle_nt_width()) {
+        case 512: add_span_nt512(a, b, c, lo, hi); break;
+        case 256: add_span_nt256(a, b, c, lo, hi); break;
+        default:  add_span_nt128(a, b, c, lo, hi); break;
+    }
+}
+#else
+int oracle_nt_width(void) { return 0; }
+static void add_span_nt(const float *a, const float *b, float *c, size_t lo, size_t hi) { add_span(a, b, c, lo, hi); }
+#endif
+
 static void *span_main(void *arg)
 {
     span_t *s = (span_t *)arg;
     if (s->op == 0) {
         add_span(s->a, s->b, s->c, s->lo, s->hi);
+    } else if (s->op == 3) {
+        add_span_nt(s->a, s->b, s->c, s->lo, s->hi);
     } else if (s->op == 1) {                               /* first-touch + fill */
         oracle_fill_ctr_f32((float *)s->a + s->lo, s->hi - s->lo, s->seed_a, s->first + s->lo);
         oracle_fill_ctr_f32((float *)s->b + s->lo, s->hi - s->lo, s->seed_b, s->first + s->lo);
@@ -311,6 +377,14 @@ void oracle_vadd_f32_mt(const float *a, const float *b, float *c, size_t n, int 
     run_spans(p, n, threads, NULL);
 }
 
+/* The same with non-temporal stores (timing variant of the CPU baseline; same bits). */
+void oracle_vadd_f32_mt_nt(const float *a, const float *b, float *c, size_t n, int threads)
+{
+    span_t p; memset(&p, 0, sizeof p);
+    p.a = a; p.b = b; p.c = c; p.op = 3;
+    run_spans(p, n, threads, NULL);
+}
+
 /* Multi-threaded ctr fill of A and B (and zero of C if non-NULL): the worker that will
  * later add a span also first-touches it. */
 void oracle_fill_ctr_pair_mt(float *a, float *b, float *c, size_t n, uint64_t seed_a,
@@ -337,8 +411,17 @@ static double now_s(void)
 
 /* Times `reps` passes of the all-cores add over n elements; writes per-pass seconds to
  * secs[reps].  Buffers are allocated and first-touched by the worker threads here. */
+int oracle_time_vadd_mt_ex(size_t n, int threads, int warmup, int reps, int nt_stores, double *secs);
+
 int oracle_time_vadd_mt(size_t n, int threads, int warmup, int reps, double *secs)
 {
+    return oracle_time_vadd_mt_ex(n, threads, warmup, reps, 0, secs);
+}
+
+/* nt_stores: 0 regular (write-allocate) stores, 1 non-temporal stores. */
+int oracle_time_vadd_mt_ex(size_t n, int threads, int warmup, int reps, int nt_stores, double *secs)
+{
+    void (*add)(const float *, const float *, float *, size_t, int) = nt_stores ? oracle_vadd_f32_mt_nt : oracle_vadd_f32_mt;
     float *a = NULL, *b = NULL, *c = NULL;
     if (posix_memalign((void **)&a, 64, n * sizeof(float) + 64) ||
         posix_memalign((void **)&b, 64, n * sizeof(float) + 64) ||
@@ -347,10 +430,10 @@ int oracle_time_vadd_mt(size_t n, int threads, int warmup, int reps, double *sec
         return -1;
     }
     oracle_fill_ctr_pair_mt(a, b, c, n, 0x0A, 0x0B, 0, threads);
-    for (int i = 0; i < warmup; ++i) oracle_vadd_f32_mt(a, b, c, n, threads);
+    for (int i = 0; i < warmup; ++i) add(a, b, c, n, threads);
     for (int i = 0; i < reps; ++i) {
         double t0 = now_s();
-        oracle_vadd_f32_mt(a, b, c, n, threads);
+        add(a, b, c, n, threads);
         secs[i] = now_s() - t0;
     }
     free(a); free(b); free(c);

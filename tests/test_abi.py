@@ -28,13 +28,24 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(capi.lib, s), f"{s} declared in include/b200va.h but not exported"
     assert set(syms) == set(capi.EXPORTED), "ctypes binding and header disagree"
-    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
-    exported = set(re.findall(r" T (b200va_\w+)", out))
-    assert exported == set(syms), exported ^ set(syms)
+    for path in (capi.LIB_PATH, capi.TUNE_LIB_PATH):          # the tune library is the same ABI, more geometries
+        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+        exported = set(re.findall(r" T (b200va_\w+)", out))
+        assert exported == set(syms), (path, exported ^ set(syms))
+    assert capi.tune_lib().b200va_abi_version() == pkg.abi_version()
+
+
+def test_struct_layouts_match_the_header():
+    """ctypes mirrors of the two structs: field order and count as declared in include/b200va.h."""
+    text = re.sub(r"/\*.*?\*/", "", open(capi.HEADER_PATH).read(), flags=re.S)
+    body = re.search(r"typedef struct b200va_tune \{(.*?)\} b200va_tune_t;", text, flags=re.S).group(1)
+    fields = re.findall(r"int\s+(\w+)\s*;", body)
+    assert fields == [n for n, _ in capi.Tune._fields_]
+    assert C.sizeof(capi.Tune) == 4 * len(fields) == 44
 
 
 def test_abi_version_and_strerror():
-    assert pkg.abi_version() == 1
+    assert pkg.abi_version() == 2
     assert pkg.strerror(0) == "success"
     for code in (-1, -2, -3, -4, -5, -6, -7):
         assert pkg.strerror(code) not in ("success", "unknown error")
@@ -47,9 +58,32 @@ def test_library_is_sm100a_only_and_uses_tma_and_256bit_accesses():
     assert archs == {"sm_100a"}, archs
     assert "UBLKCP" in sass            # cp.async.bulk (TMA)
     assert "SYNCS" in sass             # mbarrier
+    assert "UGETNEXTWORKID" in sass    # clusterlaunchcontrol.try_cancel (K2c, K1c)
+    assert "ACQBULK" in sass and "PREEXIT" in sass           # griddepcontrol.wait / launch_dependents (PDL)
     assert re.search(r"LDG\.E\S*\.256", sass) and re.search(r"STG\.E\S*\.256", sass)
     assert re.search(r"LDG\.E\S*\.128", sass)
     assert "HMMA" not in sass and "UTCHMMA" not in sass      # a stream, not a contraction
+    # "fat binary + PTX" (SURVEY.md 8(f)2): the production library also embeds its compute_100a PTX
+    ptx = subprocess.run(["cuobjdump", "-lptx", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a.ptx" in ptx, ptx
+    # the production library carries the production set, the tune library the whole matrix
+    n_prod = sass.count("Function :")
+    n_tune = subprocess.run(["cuobjdump", "-sass", capi.TUNE_LIB_PATH], capture_output=True, text=True).stdout.count("Function :")
+    assert n_prod < 200 < n_tune, (n_prod, n_tune)
+
+
+def test_early_load_variant_issues_its_loads_before_the_dependency_wait():
+    """SASS of the EARLY kernel: both LDG.E.128 come before the first ACQBULK (griddepcontrol.wait)
+    and the store after it; the plain kernel waits first."""
+    def body(early: int) -> list[str]:
+        fn = f"_ZN6b200va8vadd_vecILi4ELi1ELi0ELi1ELb{early}EEEvPKfS2_Pfmmmm"
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", fn, capi.LIB_PATH], capture_output=True, text=True).stdout
+        return re.findall(r"\b(LDG\.E\.128|STG\.E\S*\.128|ACQBULK)\b", out)
+    early, plain = body(1), body(0)
+    assert early and plain
+    assert early.index("ACQBULK") > [i for i, m in enumerate(early) if m.startswith("LDG")][1]
+    assert early.index("ACQBULK") < [i for i, m in enumerate(early) if m.startswith("STG")][0]
+    assert plain[0] == "ACQBULK"
 
 
 def test_host_rand_recipe_matches_oracle_and_known_answers():
@@ -92,6 +126,29 @@ def test_shard_ranges_tile_the_index_space(n, world):
     assert capi.lib.b200va_shard_range(n, world, world, C.byref(C.c_size_t()), C.byref(C.c_size_t())) == capi.ERR_INVALID
 
 
+def test_kernel_names_key_the_ncu_table():
+    """Tune.kernel_name() is the key bench.py uses to look up a kernel's ncu DRAM bytes: it must
+    name what the resolved geometry launches, and an unknown kernel must yield no traffic figure."""
+    import bench
+
+    t = pkg.resolve(capi.K_AUTO, 1 << 28)
+    assert t.kernel_name() == "vadd_vec<4,1,0,1,0>"
+    t.early_loads = 1
+    assert t.kernel_name() == "vadd_vec<4,1,0,1,1>"
+    assert pkg.resolve(capi.K_AUTO, 1 << 24).kernel_name() == "vadd_vec<4,2,3,0,0>"
+    assert pkg.resolve(capi.K2_TMA, 1 << 28).kernel_name() == "vadd_tma_clc<0,1>"
+    assert pkg.resolve(capi.K3_VEC256, 1 << 28).kernel_name() == "vadd_vec<8,1,0,1,0>"
+    assert pkg.resolve(capi.K0_SCALAR, 50000).kernel_name() == "vadd_scalar"
+    got, src = bench.ncu_traffic("vadd_vec<4,1,0,1,0>", 1 << 28)
+    assert got is not None and 0.9 < got / (12 * (1 << 28)) < 1.1 and src
+    assert bench.ncu_traffic("vadd_vec<4,1,0,1,0>", 1 << 20) == (None, None)      # no capture at this size
+    assert bench.ncu_traffic("vadd_made_up<1>", 1 << 28) == (None, None)
+
+
+def test_numa_node_of_a_device_is_minus_one_without_a_gpu_or_a_small_int():
+    assert -1 <= capi.lib.b200va_device_numa_node_of(0) < 64
+
+
 def test_resolve_geometry():
     for v in pkg.VARIANTS.values():
         t = pkg.resolve(v, 1 << 28)
@@ -107,6 +164,7 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
     # device entry points: error code, never a silent CPU result
     rc = capi.lib.b200va_add_f32(a.ctypes.data, a.ctypes.data, a.ctypes.data, 16, 0, None)
     assert rc != capi.OK
+    assert capi.lib.b200va_add_f32_ex(a.ctypes.data, a.ctypes.data, a.ctypes.data, 16, 0, capi.F_INPUTS_STABLE, None) != capi.OK
     out = np.full(16, -7.0, np.float32)
     with pytest.raises(pkg.B200VAError):
         va.add_host(a, a, out)
@@ -127,6 +185,7 @@ def test_cli_fails_loudly_without_a_gpu():
 
 def test_cli_rejects_bad_options():
     assert va.run_cli("--bogus").returncode == 1
+    assert va.run_cli("--host-mem", "floppy").returncode == 1
     assert va.run_cli("--mode", "sample", "--gpus", "2").returncode == 1
     assert va.run_cli("--help").returncode == 0
 

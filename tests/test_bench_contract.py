@@ -23,6 +23,9 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["value"] > 1e8 and d["steps"] == 2 and d["gpu_launches"] == 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["stores"].split(" ")[0] in ("regular", "non-temporal") and cb["stores"] in cb["sample"]   # the store kind is stated
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD        # the same string the GPU arm prints (same_config)
     assert d["e2e"] == {"value": d["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -37,3 +40,29 @@ def test_reference_arm_nonzero_ranks_exit_silently():
 def test_gpu_arm_refuses_to_run_on_cpu():
     p = subprocess.run([sys.executable, BENCH, "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
+
+
+def test_rank_to_device_mapping_spreads_ranks_over_the_sockets():
+    """bench.py maps rank -> GPU round-robin over NUMA nodes when there are fewer ranks than GPUs
+    (four ranks behind one socket got 0.63 e2e efficiency), identity otherwise."""
+    import bench
+
+    numa = [0, 0, 0, 0, 1, 1, 1, 1].__getitem__
+    assert [bench.device_for_rank(r, 4, 8, numa)[0] for r in range(4)] == [0, 4, 1, 5]
+    assert [bench.device_for_rank(r, 2, 8, numa)[0] for r in range(2)] == [0, 4]
+    assert bench.device_for_rank(0, 1, 8, numa)[0] == 0
+    assert [bench.device_for_rank(r, 8, 8, numa)[0] for r in range(8)] == list(range(8))
+    assert [bench.device_for_rank(r, 2, 4, [0, 0, 1, 1].__getitem__)[0] for r in range(2)] == [0, 2]
+    # one socket, unknown topology, or an odd split: every rank still gets its own GPU
+    assert [bench.device_for_rank(r, 2, 4, lambda i: 0)[0] for r in range(2)] == [0, 1]
+    assert [bench.device_for_rank(r, 2, 4, lambda i: -1)[0] for r in range(2)] == [0, 1]
+    got = [bench.device_for_rank(r, 5, 6, [0, 0, 0, 0, 1, 1].__getitem__)[0] for r in range(5)]
+    assert sorted(got) == sorted(set(got)) and got[:4] == [0, 4, 1, 5]
+
+
+def test_digest_constants_are_the_oracles():
+    import bench
+    import oracle
+
+    assert oracle.ctr_vadd_digest(1 << 24) == bench.DIGEST_2P24
+    assert oracle.ctr_vadd_digest(1 << 30) == bench.DIGEST_2P30

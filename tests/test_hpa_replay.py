@@ -68,3 +68,18 @@ def test_recorded_gpu_run_replays_to_the_same_decisions():
         assert (final_replicas > 1) == want_up
         if isinstance(r["target_util"], (int, float)):
             assert abs(r["nvml_util_mean"] - r["target_util"]) <= max(1.0, 0.1 * r["target_util"])   # controller accuracy
+
+
+def test_scale_down_waits_for_the_stabilization_window():
+    """kube-controller-manager's default 5-minute downscale stabilization: after the load stops the
+    replicas stay up until every recommendation of the last 300 s is lower; scale-ups are immediate."""
+    trace = {f"cuda-test-{i}": [(t, 97.0 if t < 60 else 1.0) for t in range(0, 600)] for i in range(3)}
+    ev = hr.Replay().run(trace, 600)
+    up = [t for t, _, r in ev if r == 3]
+    assert up and up[0] <= 30                                       # straight to maxReplicas
+    first_down = min(t for t, _, r in ev if t > 60 and r < 3)
+    assert 60 + 300 <= first_down <= 60 + 300 + 3 * hr.HPA_SYNC_S   # not before the window has passed
+    assert ev[-1][2] == 1
+    # without the window the same trace drops at the next sync
+    ev0 = hr.Replay(downscale_stabilization_s=0.0).run(trace, 600)
+    assert min(t for t, _, r in ev0 if t > 60 and r < 3) <= 60 + hr.DCGM_INTERVAL_S + 2 * hr.HPA_SYNC_S

@@ -149,3 +149,24 @@ def test_empty_inputs():
     assert oracle.vadd(e, e).size == 0
     assert oracle.bits_digest(e) == (0, 0)
     assert oracle.ctr_vadd_digest(0) == (0, 0)
+
+
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 1000, 100_003])
+def test_non_temporal_timing_variant_returns_the_same_bits(n):
+    """The CPU baseline's non-temporal-store leg (vaddps + movntps, widest ISA of the host) is a
+    timing variant only: bit-identical to the scalar restatement, specials included."""
+    rng = np.random.default_rng(n)
+    ua = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    ub = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    a, b = ua.view(np.float32), ub.view(np.float32)
+    assert oracle.nt_width() in (128, 256, 512)
+    for threads in (1, 3):
+        got = oracle.vadd_mt_nt(a[1:], b[1:], threads) if n > 1 else oracle.vadd_mt_nt(a, b, threads)   # misaligned start too
+        want = oracle.vadd(np.ascontiguousarray(a[1:]), np.ascontiguousarray(b[1:])) if n > 1 else oracle.vadd(a, b)
+        assert oracle.first_mismatch_bits(got, want, "f32") == -1
+
+
+def test_cpu_baseline_reports_both_store_kinds():
+    cfg = oracle.best_cpu_config(1 << 20)
+    assert set(k.split(" ")[0] for k in cfg["tried"]) == {"regular", "non-temporal"}
+    assert cfg["rate"] == max(d["elements_per_s"] for d in cfg["tried"].values()) and cfg["threads"] >= 1
