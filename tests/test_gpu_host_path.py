@@ -52,6 +52,90 @@ def test_stager_pageable_mode_on_plain_numpy_arrays():
                 assert (hc[m:] == -1.0).all()
 
 
+def test_stager_register_once_on_plain_malloced_arrays():
+    """Mode 4 / AUTO: pageable arrays are page-locked in place on first sight, the registration is
+    cached by address range, and later calls run the pinned lanes pipeline on the same arrays."""
+    n = 12_000_017
+    ha, hb = oracle.fill_ctr(n, 0x0A, 21), oracle.fill_ctr(n, 0x0B, 21)
+    want = oracle.vadd(ha, hb)
+    hc = np.full(n, -1.0, np.float32)
+
+    with va.Stager(0, 1 << 21, 3) as st:
+        ms_first = st.add(ha, hb, hc, mode=capi.STAGE_AUTO)
+        assert st.last_mode == capi.STAGE_REGISTER and ms_first > 0
+        assert oracle.first_mismatch(hc, want) == -1
+        for m in (n, n - 7, 1 << 20):                         # sub-ranges of the cached registrations
+            hc.fill(-1.0)
+            st.add(ha[:m], hb[:m], hc[:m], mode=capi.STAGE_AUTO)
+            assert st.last_mode == capi.STAGE_REGISTER
+            assert oracle.first_mismatch(hc[:m].copy(), want[:m].copy()) == -1 and (hc[m:] == -1.0).all()
+        # a pinned array is recognised as such (no double registration), tiny arrays take the bounce ring
+        pc = torch.empty(n, dtype=torch.float32).pin_memory()
+        st.add(ha, hb, pc, mode=capi.STAGE_REGISTER)
+        assert oracle.first_mismatch(pc.numpy(), want) == -1
+        small = np.full(1000, -1.0, np.float32)
+        st.add(ha[:1000].copy(), hb[:1000].copy(), small, mode=capi.STAGE_AUTO)
+        assert st.last_mode == capi.STAGE_BOUNCE and oracle.first_mismatch(small, want[:1000].copy()) == -1
+        # explicit release: the arrays are ordinary pageable memory again and can be re-registered
+        st.release_host()
+        hc.fill(-1.0)
+        st.add(ha, hb, hc, mode=capi.STAGE_AUTO)
+        assert st.last_mode == capi.STAGE_REGISTER and oracle.first_mismatch(hc, want) == -1
+        # a new array overlapping a cached range (here: a window that starts inside ha and runs past its
+        # registered sub-range) replaces the stale registration instead of failing
+        st.release_host()
+        st.add(ha[:n // 2], hb[:n // 2], hc[:n // 2], mode=capi.STAGE_REGISTER)
+        st.add(ha, hb, hc, mode=capi.STAGE_REGISTER)
+        assert oracle.first_mismatch(hc, want) == -1
+    # the stager unregistered everything on destroy: registering by hand works again
+    rt = torch.cuda.cudart()
+    assert int(rt.cudaHostRegister(ha.ctypes.data, ha.nbytes, 0)) == 0
+    assert int(rt.cudaHostUnregister(ha.ctypes.data)) == 0
+    # pinned arrays through AUTO pick the lanes pipeline
+    pa = torch.from_numpy(ha).pin_memory()
+    pb = torch.from_numpy(hb).pin_memory()
+    with va.Stager(0, 1 << 21, 3) as st:
+        st.add(pa, pb, pc, mode=capi.STAGE_AUTO)
+        assert st.last_mode == capi.STAGE_LANES and oracle.first_mismatch(pc.numpy(), want) == -1
+        with pytest.raises(capi.B200VAError):
+            st.add(pa, pb, pc, mode=9)
+
+
+def test_stager_restores_the_callers_current_device():
+    """Entry points that take a `device` leave the calling thread on the device it was on."""
+    n = 1 << 20
+    ha, hb = oracle.fill_ctr(n, 0x0A), oracle.fill_ctr(n, 0x0B)
+    last = torch.cuda.device_count() - 1
+    before = torch.cuda.current_device()
+    for target in {0, last}:
+        out = va.add_host(ha, hb, device=target)
+        assert oracle.first_mismatch(out, oracle.vadd(ha, hb)) == -1
+        with va.Stager(target, 1 << 18, 2) as st:
+            hc = np.empty_like(ha)
+            st.add(ha, hb, hc, mode=capi.STAGE_BOUNCE)
+            assert oracle.first_mismatch(hc, oracle.vadd(ha, hb)) == -1
+        assert torch.cuda.current_device() == before
+        # and a device call right after lands on the caller's device, not on `target`
+        x = torch.ones(1024, device=f"cuda:{before}")
+        y = va.add(x, x)
+        assert y.device.index == before and float(y.sum()) == 2048.0
+
+
+def test_stager_error_in_the_middle_leaves_nothing_in_flight():
+    """A failing call (zero-copy mode on pageable arrays: the runtime refuses the pointer) returns an
+    error code, and the stager is usable right after -- nothing is still running on its streams."""
+    n = 1 << 22
+    ha, hb = oracle.fill_ctr(n, 0x0A), oracle.fill_ctr(n, 0x0B)
+    hc = np.empty_like(ha)
+    with va.Stager(0, 1 << 20, 3) as st:
+        with pytest.raises(capi.B200VAError):
+            st.add(ha, hb, hc, mode=capi.STAGE_ZEROCOPY)
+        st.add(ha, hb, hc, mode=capi.STAGE_BOUNCE)
+        assert oracle.first_mismatch(hc, oracle.vadd(ha, hb)) == -1
+    x = torch.ones(16, device="cuda")
+    assert float(va.add(x, x).sum()) == 32.0                 # no latched CUDA error either
+
+
 def test_cli_zero_arguments_is_the_reference_process():
     """`./vectorAdd` exactly as cuda-test-deployment.yaml:19 runs it."""
     p = va.run_cli()
@@ -105,10 +189,22 @@ def test_cli_seed_changes_the_data_not_the_verdict():
     assert len(digests) == 2
 
 
+def test_cli_verify_none_never_claims_a_pass():
+    p = va.run_cli("--n", "4096", "--verify", "none")
+    assert p.returncode == 0 and "Test PASSED" not in p.stdout and "Test SKIPPED" in p.stdout and "Done" in p.stdout
+
+
 def test_cli_staged_mode_and_duty_cycle():
     p = va.run_cli("--mode", "staged", "--n", str((1 << 23) + 1), "--iters", "2")
     assert p.returncode == 0, p.stderr
-    assert json.loads(p.stdout.strip().splitlines()[-1])["mismatches"] == 0
+    r = json.loads(p.stdout.strip().splitlines()[-1])
+    assert r["mismatches"] == 0 and r["stage_mode"] == capi.STAGE_LANES and r["host_mem"].startswith("pinned")
+    # the reference process's own kind of memory: malloc'd arrays, page-locked once by the stager
+    p = va.run_cli("--mode", "staged", "--host-mem", "pageable", "--n", str((1 << 23) + 1), "--iters", "3")
+    assert p.returncode == 0, p.stderr
+    r = json.loads(p.stdout.strip().splitlines()[-1])
+    assert r["mismatches"] == 0 and r["stage_mode"] == capi.STAGE_REGISTER and r["host_mem"].startswith("pageable")
+    assert r["first_pass_wall_ms"] > 0
     import tempfile
 
     with tempfile.TemporaryDirectory() as d:
@@ -117,10 +213,23 @@ def test_cli_staged_mode_and_duty_cycle():
         assert p.returncode == 0, p.stderr
         r = json.loads(p.stdout.strip().splitlines()[-1])
         assert r["mismatches"] == 0 and 0.2 < r["gpu_busy_frac"] < 0.4
+        # the CLI's verdict is the HPA's: outside the 10 % tolerance band only
+        assert r["hpa_would_scale"] == (r["nvml_util_mean"] > r["hpa_threshold"] * 1.1)
+        from k8s_gpu_hpa_b200 import hpa_replay
+        assert r["hpa_would_scale"] == hpa_replay.would_scale_up(r["nvml_util_mean"])
         text = open(prom).read()                       # the series the reference's recording rule reads
         assert "# TYPE dcgm_gpu_utilization gauge" in text
         sample = [l for l in text.splitlines() if l.startswith("dcgm_gpu_utilization{")][0]
         assert 'gpu="0"' in sample and "uuid=\"GPU-" in sample and 0 <= int(sample.rsplit(" ", 1)[1]) <= 100
+        assert 'namespace="default"' in sample
+    import os
+    with tempfile.TemporaryDirectory() as d:
+        prom = d + "/gpu.prom"
+        import subprocess
+        p = subprocess.run([capi.CLI_PATH, "--n", "2^20", "--iters", "20", "--duration", "0.8", "--metrics-file", prom],
+                           capture_output=True, text=True, timeout=120, env=dict(os.environ, POD_NAMESPACE="gpu-demo"))
+        assert p.returncode == 0, p.stderr
+        assert 'namespace="gpu-demo"' in open(prom).read()
 
 
 @pytest.mark.parametrize("gpus", [2, 4, 8])

@@ -146,6 +146,8 @@ def test_argument_errors():
     t = capi.Tune(kind=capi.K2_TMA, threads=256, stages=64, tile_bytes=1 << 20, store_mode=1)
     with pytest.raises(pkg.B200VAError):
         va.add(a, a, tune=t)
+    with pytest.raises(pkg.B200VAError):
+        va.add(a, a, tune=capi.Tune(kind=capi.K1_VEC128, threads=128, unroll=2, early_loads=7))
 
 
 def test_tuned_geometries_are_all_bit_exact():
@@ -179,19 +181,127 @@ def test_tuned_geometries_are_all_bit_exact():
     for threads in (32, 256, 1024):                                  # 4-byte accesses, U loads per array in flight
         for unroll in (4, 8, 16):
             geos.append(capi.Tune(kind=capi.K4_SCALAR_MLP, threads=threads, unroll=unroll))
+    for kind in (capi.K1_VEC128, capi.K3_VEC256):                    # early loads and the CLC scheduler (K1c)
+        for early in (0, 1):
+            for unroll in (1, 2, 4, 8):
+                for threads in (64, 256, 512):
+                    geos.append(capi.Tune(kind=kind, threads=threads, unroll=unroll, ld_hint=0, st_hint=1, early_loads=early, scheduler=1))
+            geos.append(capi.Tune(kind=kind, threads=128, unroll=2, ctas_per_sm=2, ld_hint=3, st_hint=0, early_loads=early))
     for t in geos:
         out = torch.full((n,), -1.0, dtype=torch.float32, device="cuda")
         if t.kind == capi.K4_SCALAR_MLP and t.threads == 1024 and t.unroll == 16:
             with pytest.raises(pkg.B200VAError) as e:        # 1024 threads x 32 live loads: register-limited, refused
-                va.add(a, b, out, tune=t)
+                va.add(a, b, out, tune=t, full_matrix=True)
             assert e.value.code == capi.ERR_VARIANT
             va.add(a, b, out)                                  # and the refusal leaves no latched CUDA error behind
             torch.cuda.synchronize()
             assert_bits_equal(out, want, "after refused launch")
             continue
-        va.add(a, b, out, tune=t)
+        va.add(a, b, out, tune=t, full_matrix=True)
         torch.cuda.synchronize()
         assert_bits_equal(out, want, str(t.as_dict()))
+
+
+def test_production_library_carries_the_production_set_only():
+    """libb200va.so: what AUTO and the named variants resolve to (+ early loads, + K1c) runs; a
+    geometry only the A/B matrix has is refused with ERR_VARIANT -- and runs in libb200va_tune.so."""
+    n = 300_003
+    ha, hb = oracle.fill_ctr(n, 0x0A), oracle.fill_ctr(n, 0x0B)
+    want = oracle.vadd(ha, hb)
+    a, b = dev(ha), dev(hb)
+    for size in (1 << 10, 1 << 20, 1 << 22, 1 << 24, 1 << 28):
+        for v in pkg.VARIANTS.values():
+            t = pkg.resolve(v, size)                      # the geometry of that size class, run on our n
+            for early in (0, 1):
+                t.early_loads = early
+                out = torch.full((n,), -1.0, dtype=torch.float32, device="cuda")
+                va.add(a, b, out, tune=t)
+                assert_bits_equal(out, want, str(t.as_dict()))
+    for t in (capi.Tune(kind=capi.K1_VEC128, threads=256, unroll=2, st_hint=1, scheduler=1),
+              capi.Tune(kind=capi.K1_VEC128, threads=256, unroll=4, st_hint=1, scheduler=1, early_loads=1)):
+        out = torch.full((n,), -1.0, dtype=torch.float32, device="cuda")
+        va.add(a, b, out, tune=t)
+        assert_bits_equal(out, want, str(t.as_dict()))
+    exotic = capi.Tune(kind=capi.K1_VEC128, threads=256, unroll=8, ld_hint=2, st_hint=2)
+    with pytest.raises(pkg.B200VAError) as e:
+        va.add(a, b, tune=exotic)
+    assert e.value.code == capi.ERR_VARIANT
+    assert_bits_equal(va.add(a, b, tune=exotic, full_matrix=True), want, "tune library")
+
+
+def test_early_loads_chain_of_launches_is_bit_exact():
+    """B200VA_F_INPUTS_STABLE: back-to-back launches whose loads run ahead of the dependency on the
+    previous launch.  Rotating disjoint buffer sets (the stager's / sweep's shape), the same set
+    repeatedly (the launch loop's shape), and a consumer chain C -> next launch's A, where the
+    flag must NOT be given -- stream order of C has to hold either way."""
+    n = (1 << 22) + 5
+    sets = 5
+    A = [torch.empty(n, dtype=torch.float32, device="cuda") for _ in range(sets)]
+    B = [torch.empty_like(A[0]) for _ in range(sets)]
+    Cs = [torch.zeros_like(A[0]) for _ in range(sets)]
+    for s in range(sets):
+        va.fill_ctr(A[s], 0x0A, s * n)
+        va.fill_ctr(B[s], 0x0B, s * n)
+    torch.cuda.synchronize()
+    for variant in ("auto", "k1", "k3", "k2", "k0"):
+        for c in Cs:
+            c.zero_()
+        for i in range(40):
+            s = i % sets
+            va.add(A[s], B[s], Cs[s], variant=variant, inputs_stable=True)
+        for s in range(sets):
+            assert va.verify(A[s], B[s], Cs[s]) == (0, -1), (variant, s)
+            assert va.digest(Cs[s]) == oracle.ctr_vadd_digest(n, s * n)
+        # same buffers every launch
+        for _ in range(30):
+            va.add(A[0], B[0], Cs[1], variant=variant, inputs_stable=True)
+        assert va.verify(A[0], B[0], Cs[1]) == (0, -1)
+    # write-after-write order on C is kept: the later launch's values must win
+    for _ in range(20):
+        va.add(A[0], B[0], Cs[0], inputs_stable=True)
+        va.add(A[1], B[1], Cs[0], inputs_stable=True)
+    assert va.verify(A[1], B[1], Cs[0]) == (0, -1)
+    # aliasing: the hint is dropped inside the library (C == A feeds the next launch)
+    x = A[2].clone()
+    for _ in range(8):
+        va.add(x, B[2], x, inputs_stable=True)
+    ref = oracle.fill_ctr(n, 0x0A, 2 * n)
+    hb = oracle.fill_ctr(n, 0x0B, 2 * n)
+    for _ in range(8):
+        ref = oracle.vadd(ref, hb)
+    assert_bits_equal(x, ref, "in-place chain")
+    assert capi.lib.b200va_add_f32_ex(x.data_ptr(), x.data_ptr(), x.data_ptr(), n, 0, 0x80, None) == capi.ERR_INVALID
+
+
+def test_vec_kernel_under_cluster_launch_control_ragged_sizes_and_offsets():
+    """K1c: the vec tile body with tiles handed out by try_cancel -- every tile exactly once, the
+    scalar head/tail travel with tile 0 whichever CTA runs it."""
+    nmax = max(SIZES)
+    ha, hb = oracle.fill_ctr(nmax + 8, 0x0A, 78), oracle.fill_ctr(nmax + 8, 0x0B, 78)
+    a, b = dev(ha), dev(hb)
+    for t in (capi.Tune(kind=capi.K1_VEC128, threads=256, unroll=2, st_hint=1, scheduler=1),
+              capi.Tune(kind=capi.K1_VEC128, threads=64, unroll=4, st_hint=1, scheduler=1, early_loads=1),
+              capi.Tune(kind=capi.K3_VEC256, threads=32, unroll=1, st_hint=1, scheduler=1)):
+        for n in SIZES:
+            for off in (0, 1, 3):
+                out = torch.full((n + 16,), -3.0, dtype=torch.float32, device="cuda")
+                va.add(a[off:off + n], b[off:off + n], out[off:off + n], tune=t, full_matrix=True)
+                torch.cuda.synchronize()
+                assert_bits_equal(out[off:off + n], oracle.vadd(ha[off:off + n].copy(), hb[off:off + n].copy()), f"k1c n={n} off={off}")
+                assert (out[:off] == -3.0).all() and (out[off + n:] == -3.0).all()
+    n = 1 << 24
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    y = torch.empty_like(x)
+    z = torch.empty_like(x)
+    va.fill_ctr(x, 0x0A)
+    va.fill_ctr(y, 0x0B)
+    t = capi.Tune(kind=capi.K1_VEC128, threads=256, unroll=2, st_hint=1, scheduler=1, early_loads=1)
+    for _ in range(50):
+        va.add(x, y, z, tune=t)
+    assert va.digest(z) == oracle.ctr_vadd_digest(n) and va.verify(x, y, z) == (0, -1)
+    # ctas_per_sm (static persistent split) and the CLC scheduler exclude each other
+    with pytest.raises(pkg.B200VAError):
+        va.add(x, y, z, tune=capi.Tune(kind=capi.K1_VEC128, threads=256, unroll=2, st_hint=1, scheduler=1, ctas_per_sm=2))
 
 
 def test_clc_scheduled_tma_kernel_ragged_sizes_and_offsets():

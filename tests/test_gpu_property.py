@@ -36,13 +36,13 @@ def pools():
 
 @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(n=st.one_of(st.integers(0, 70), st.integers(0, POOL)), oa=st.integers(0, 9), ob=st.integers(0, 9),
-       oc=st.integers(0, 9), variant=st.sampled_from(["auto", "k0", "k1", "k2", "k3"]), same=st.booleans())
-def test_random_lengths_offsets_variants(pools, n, oa, ob, oc, variant, same):
+       oc=st.integers(0, 9), variant=st.sampled_from(["auto", "k0", "k1", "k2", "k3"]), same=st.booleans(), stable=st.booleans())
+def test_random_lengths_offsets_variants(pools, n, oa, ob, oc, variant, same, stable):
     ha, hb, a, b = pools
     if same:
         ob = oc = oa            # equal misalignment: vector body with peeled head
     out = torch.full((n + 32,), -3.0, dtype=torch.float32, device="cuda")
-    va.add(a[oa:oa + n], b[ob:ob + n], out[oc:oc + n], variant=variant)
+    va.add(a[oa:oa + n], b[ob:ob + n], out[oc:oc + n], variant=variant, inputs_stable=stable)
     torch.cuda.synchronize()
     got = out.cpu().numpy()
     want = oracle.vadd(ha[oa:oa + n].copy(), hb[ob:ob + n].copy())
@@ -53,13 +53,13 @@ def test_random_lengths_offsets_variants(pools, n, oa, ob, oc, variant, same):
 @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(n=st.integers(1, POOL), threads=st.sampled_from([32, 64, 96, 128, 256, 320, 512, 1024]),
        unroll=st.sampled_from([1, 2, 4, 8]), cps=st.sampled_from([0, 1, 3]), ld=st.integers(0, 5), stt=st.integers(0, 3),
-       wide=st.booleans())
-def test_random_vec_geometries(pools, n, threads, unroll, cps, ld, stt, wide):
+       wide=st.booleans(), early=st.booleans(), clc=st.booleans())
+def test_random_vec_geometries(pools, n, threads, unroll, cps, ld, stt, wide, early, clc):
     ha, hb, a, b = pools
-    t = capi.Tune(kind=capi.K3_VEC256 if wide else capi.K1_VEC128, threads=threads, unroll=unroll, ctas_per_sm=cps,
-                  ld_hint=ld, st_hint=stt)
+    t = capi.Tune(kind=capi.K3_VEC256 if wide else capi.K1_VEC128, threads=threads, unroll=unroll, ctas_per_sm=0 if clc else cps,
+                  ld_hint=ld, st_hint=stt, early_loads=int(early), scheduler=int(clc))
     try:
-        out = va.add(a[:n], b[:n], tune=t)
+        out = va.add(a[:n], b[:n], tune=t, full_matrix=True)
     except capi.B200VAError as e:
         # the only legal refusal: a register-limited CTA size (1024 threads x 16 live 256-bit vectors)
         assert e.code == capi.ERR_VARIANT and threads == 1024 and unroll == 8
@@ -78,9 +78,9 @@ def test_random_tma_geometries(pools, n, threads, stages, tile_k, mode, hint):
     ring = stages * 2 * tile_k + (44 * stages + 16 if mode == 2 else 16 * stages)
     if ring > 227 * 1024:           # does not fit the 227 KiB opt-in shared memory: must be refused, not launched
         with pytest.raises(capi.B200VAError) as e:
-            va.add(a[:n], b[:n], tune=t)
+            va.add(a[:n], b[:n], tune=t, full_matrix=True)
         assert e.value.code == capi.ERR_VARIANT
         return
-    out = va.add(a[:n], b[:n], tune=t)
+    out = va.add(a[:n], b[:n], tune=t, full_matrix=True)
     torch.cuda.synchronize()
     assert oracle.first_mismatch(out.cpu().numpy(), oracle.vadd(ha[:n].copy(), hb[:n].copy())) == -1

@@ -31,6 +31,36 @@ elif which == "clc":
                              (4, 4096), (8, 4096), (2, 32768), (3, 32768), (12, 8192), (6, 32768)):
             for ld, st in ((0, 1), (3, 1), (0, 0)):
                 print(K2, threads, 0, 1, ld, st, stages, tile, 2)
+elif which == "cold":
+    # r02: cold (rotating-buffer) mid sizes -- what closes the launch-boundary bubble: early loads,
+    # the CLC scheduler (K1c), whole-wave persistent grids, next to the r01 AUTO classes
+    for early in (0, 1):
+        for threads, unroll in ((128, 1), (256, 1), (512, 1), (1024, 1), (128, 2), (256, 2), (512, 2), (128, 4), (256, 4)):
+            for ld, st in ((0, 0), (0, 1), (3, 0)):
+                print(K1, threads, unroll, 0, ld, st, 0, 0, 0, early, 0)
+        for threads, unroll in ((256, 1), (512, 1), (256, 2)):
+            print(K3, threads, unroll, 0, 0, 1, 0, 0, 0, early, 0)
+        for threads, unroll in ((128, 2), (256, 2), (512, 2), (128, 4), (256, 4), (512, 4), (256, 8)):       # K1c
+            for st in (0, 1):
+                print(K1, threads, unroll, 0, 0, st, 0, 0, 0, early, 1)
+        for threads, unroll, cps in ((256, 2, 8), (512, 1, 4), (256, 4, 8), (512, 2, 4), (256, 2, 4)):   # whole-wave persistent
+            print(K1, threads, unroll, cps, 0, 1, 0, 0, 0, early, 0)
+    for threads, stages in ((128, 3), (256, 4), (512, 8)):
+        print(K2, threads, 0, 1, 0, 1, stages, 8192, 2)
+elif which == "headline":
+    # r02: 2^28 -- the production geometry, its early-load twin, K1c, and the r01 runners-up
+    for early in (0, 1):
+        for threads, unroll in ((512, 1), (384, 1), (256, 1), (1024, 1), (256, 2), (512, 2)):
+            print(K1, threads, unroll, 0, 0, 1, 0, 0, 0, early, 0)
+        for threads, unroll in ((256, 2), (512, 2), (256, 4), (512, 4), (128, 4), (256, 8)):
+            print(K1, threads, unroll, 0, 0, 1, 0, 0, 0, early, 1)
+        print(K3, 768, 2, 0, 0, 1, 0, 0, 0, early, 0)
+    print(K2, 512, 0, 1, 0, 1, 8, 8192, 2)
+elif which == "skew":
+    # r02 channel-phase experiment: only the production kernel and the control
+    print(K1, 512, 1, 0, 0, 1, 0, 0, 0, 0, 0)
+    print(K1, 512, 1, 0, 0, 1, 0, 0, 0, 1, 0)
+    print(K3, 768, 2, 0, 0, 1, 0, 0, 0, 0, 0)
 else:
     # round 2: thread counts around the winner, the L2::256B load hint, a few TMA shapes
     for kind in (K1, K3):

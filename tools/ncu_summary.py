@@ -1,9 +1,13 @@
 #!/usr/bin/env python
 """Summarise .ncu-rep captures (read here, no GPU needed) into JSON + markdown for profiles/.
 
-    python tools/ncu_summary.py gpurun_out/r01/prof_auto.ncu-rep [more.ncu-rep ...] --out profiles/r01
+    python tools/ncu_summary.py gpurun_out/r01/prof_auto.ncu-rep [more.ncu-rep ...] --out profiles/r01 [--n N] [--table]
+
+--table also merges one row per (kernel, n) into profiles/ncu_summary.json, the per-kernel table
+bench.py reads roofline.traffic from (key "<kernel>@<n>", kernel as Tune.kernel_name()).
 """
 import argparse
+import re
 import csv
 import io
 import json
@@ -72,8 +76,39 @@ def read_raw(rep: str):
     return res
 
 
+def canonical(name: str) -> str:
+    """'void b200va::vadd_vec<(int)4, (int)1, (int)0, (int)1, (bool)0>(const float *, ...)' -> 'vadd_vec<4,1,0,1,0>'"""
+    name = re.sub(r"\(.*?\)(?=\s*\d|\s*true|\s*false)", "", name.split("(const")[0].split("(float")[0])
+    name = name.replace("void ", "").replace("b200va::", "").replace("true", "1").replace("false", "0")
+    return re.sub(r"\s+", "", name)
+
+
+def merge_table(rows, n: int, path: str) -> None:
+    try:
+        doc = json.load(open(path))
+    except Exception:
+        doc = {"kernels": {}}
+    groups = {}
+    for d in rows:
+        if "dram_bytes" in d:
+            groups.setdefault(canonical(d["kernel"]), []).append(d)
+    for k, g in groups.items():
+        mean = lambda key: sum(x[key] for x in g if key in x) / max(1, sum(1 for x in g if key in x))  # noqa: E731
+        doc["kernels"][f"{k}@{n}"] = {
+            "kernel": "b200va::" + k, "source": "profiles/" + "/".join(g[0]["report_path"].split("/")[-2:]) + " (ncu --set full --clock-control none)",
+            "launches_captured": len(g), "dram_bytes_per_launch": mean("dram_bytes"), "dram_read_bytes_per_launch": mean("dram_read_bytes"),
+            "dram_write_bytes_per_launch": mean("dram_write_bytes"), "algorithmic_bytes_per_launch": 12 * n,
+            "traffic_over_algorithmic": mean("dram_bytes") / (12 * n), "duration_us": [x["duration_ns"] / 1e3 for x in g],
+            "dram_pct_of_pin_peak": [x.get("dram_pct_of_peak") for x in g], "busiest_channel_pct": [x.get("dram_busiest_channel_pct") for x in g],
+            "idlest_channel_pct": [x.get("dram_idlest_channel_pct") for x in g], "l2_hit_rate_pct": [x.get("l2_hit_rate_pct") for x in g],
+            "registers_per_thread": g[0].get("registers_per_thread"), "grid": g[0].get("grid"), "block": g[0].get("block"),
+            "achieved_occupancy_pct": [x.get("achieved_occupancy_pct") for x in g]}
+    json.dump(doc, open(path, "w"), indent=1)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--table", action="store_true", help="merge into profiles/ncu_summary.json")
     ap.add_argument("reps", nargs="+")
     ap.add_argument("--out", required=True, help="output prefix (writes <out>_ncu.json and <out>_ncu.md)")
     ap.add_argument("--n", type=int, default=1 << 28)
@@ -82,12 +117,17 @@ def main():
     for rep in args.reps:
         for d in read_raw(rep):
             d["report"] = os.path.basename(rep)
+            d["report_path"] = os.path.abspath(rep)
             d["algorithmic_bytes"] = 12 * args.n
             if d.get("duration_ns"):
                 d["algorithmic_GBps"] = d["algorithmic_bytes"] / d["duration_ns"]
             if d.get("dram_bytes"):
                 d["traffic_over_algorithmic"] = d["dram_bytes"] / d["algorithmic_bytes"]
             allk.append(d)
+    if args.table:
+        merge_table(allk, args.n, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_summary.json"))
+    for d in allk:
+        d.pop("report_path", None)
     json.dump(allk, open(args.out + "_ncu.json", "w"), indent=1)
     cols = ["report", "kernel", "grid", "block", "registers_per_thread", "dyn_smem_bytes", "duration_ns", "algorithmic_GBps",
             "dram_GBps", "dram_bytes", "traffic_over_algorithmic", "dram_pct_of_peak", "l2_hit_rate_pct",
