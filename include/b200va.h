@@ -105,8 +105,10 @@ int         b200va_abi_version(void);
 const char *b200va_strerror(int code);
 /* Attributes of `device` (does not change the current device). */
 int         b200va_query(int device, b200va_devinfo_t *out);
-/* The geometry B200VA_K_AUTO (or a named variant) resolves to for n elements. */
+/* The geometry B200VA_K_AUTO (or a named variant) resolves to for n elements; the _ex form
+ * takes the B200VA_F_* hints b200va_add_f32_ex takes. */
 int         b200va_resolve(int variant, size_t n, b200va_tune_t *out);
+int         b200va_resolve_ex(int variant, size_t n, unsigned flags, b200va_tune_t *out);
 
 /* Launch geometry a tune resolves to on `device` for n elements with 32-byte-aligned
  * pointers (what "CUDA kernel launch with %d blocks of %d threads" prints, a5). */
@@ -129,6 +131,10 @@ int b200va_add_f32_tuned(const float *dA, const float *dB, float *dC, size_t n,
  * ~2 us bubble between back-to-back launches.  Results and stream order of C are
  * unchanged; the flag is ignored when C aliases A or B. */
 #define B200VA_F_INPUTS_STABLE 1u
+/* B200VA_F_COLD: the operands are not L2-resident (fresh from a copy engine, or one of many
+ * buffer sets touched in rotation): B200VA_K_AUTO then resolves to the geometry tuned on
+ * rotating buffers instead of the one tuned for relaunching the same buffers.  A hint only. */
+#define B200VA_F_COLD          2u
 int b200va_add_f32_ex(const float *dA, const float *dB, float *dC, size_t n,
                       int variant, unsigned flags, void *stream);
 

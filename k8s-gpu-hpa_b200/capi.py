@@ -23,7 +23,7 @@ OK = 0
 ERR_INVALID, ERR_ALIGN, ERR_OVERLAP, ERR_VARIANT, ERR_NO_DEVICE, ERR_VERIFY, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 ERR_CUDA_BASE = -1000
 K_AUTO, K0_SCALAR, K1_VEC128, K2_TMA, K3_VEC256, K4_SCALAR_MLP = 0, 1, 2, 3, 4, 5
-F_INPUTS_STABLE = 1
+F_INPUTS_STABLE, F_COLD = 1, 2
 STAGE_AUTO, STAGE_SLOTS, STAGE_ZEROCOPY, STAGE_LANES, STAGE_BOUNCE, STAGE_REGISTER = -1, 0, 1, 2, 3, 4
 OPS = {"copy": 0, "scale": 1, "add": 2, "triad": 3}
 DTYPES = {"f32": 0, "f64": 1, "f16": 2, "bf16": 3}
@@ -78,6 +78,7 @@ _SIGS = {
     "b200va_strerror": (C.c_char_p, [_I]),
     "b200va_query": (_I, [_I, C.POINTER(DevInfo)]),
     "b200va_resolve": (_I, [_I, _SZ, C.POINTER(Tune)]),
+    "b200va_resolve_ex": (_I, [_I, _SZ, C.c_uint, C.POINTER(Tune)]),
     "b200va_geometry": (_I, [C.POINTER(Tune), _SZ, _I, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "b200va_add_f32": (_I, [_P, _P, _P, _SZ, _I, _P]),
     "b200va_add_f32_tuned": (_I, [_P, _P, _P, _SZ, C.POINTER(Tune), _P]),
@@ -150,9 +151,9 @@ def query(device: int = 0) -> DevInfo:
     return info
 
 
-def resolve(variant: int, n: int) -> Tune:
+def resolve(variant: int, n: int, flags: int = 0) -> Tune:
     t = Tune()
-    check(lib.b200va_resolve(variant, n, C.byref(t)), "b200va_resolve")
+    check(lib.b200va_resolve_ex(variant, n, flags, C.byref(t)), "b200va_resolve_ex")
     return t
 
 

@@ -233,16 +233,27 @@ int ensure_smem_optin(tma_fn fn, int device, int bytes)
 }
 
 // ----------------------------------------------------------------------- geometry
-// Production choices per size class, from the interleaved A/B sweeps on B200
-// (profiles/r01/{b,c}_ab_2p*.jsonl; median of 7 rounds of back-to-back launches).  K_AUTO is
-// always the 128-bit kernel; thread count / unroll / cache hints follow the footprint:
+// Production choices per size class.  K_AUTO is always the 128-bit kernel; thread count / unroll /
+// cache hints follow the footprint AND what the caller says about the data:
+//
+//  default (the same buffers may be launched again: the a1 loop; profiles/r01/{b,c}_ab_2p*.jsonl, hot A/B)
 //   n >= 2^25       HBM streaming         512 thr x1, stores skip L1            7.23 TB/s @2^28, 7.14 @2^26, 7.00 @2^25
-//   2^23 < n < 2^25 footprint ~ 1-3 x L2  128 thr x2, L2 evict-first loads      7.33 TB/s @2^24
+//   2^23 < n < 2^25 footprint ~ 1-3 x L2  128 thr x2, L2 evict-first loads      7.33 TB/s @2^24 (7.47 with early loads)
 //   2^21..2^23      L2-resident           256 thr x2, plain hints (L2 keeps it) 11.7 TB/s @2^22 (an L2 number)
 //   n < 2^21        launch-bound          512 thr (>= 2^19) / 128 thr, x1
-void default_tune(int variant, size_t n, b200va_tune_t* t)
+//
+//  B200VA_F_COLD (operands not in L2: the stager's chunks, rotating buffers; profiles/r02/cold_2p*.jsonl,
+//  A/B on >= 4 x L2 of rotating buffer sets) -- one vector per thread wins, the evict-first policy and x2 lose:
+//   2^23 <= n < 2^25   512 thr x1   6.42 TB/s @2^23, 6.81 @2^24   (hot-tuned classes: 6.26 / 6.46)
+//   2^21 <= n < 2^23   256 thr x1   4.81 TB/s @2^21, 5.81 @2^22   (4.62 / 5.75)
+//  B200VA_F_COLD | B200VA_F_INPUTS_STABLE (early loads hide the next launch's DRAM ramp behind this one's tail)
+//   2^22 <= n < 2^25   256 thr x1   6.53 TB/s @2^22, 6.94 @2^23, 7.07 @2^24
+//   n < 2^22           256 thr x4   6.90 TB/s @2^21 (twice the bytes in flight per CTA for the short grid)
+void default_tune(int variant, size_t n, b200va_tune_t* t, unsigned flags = 0)
 {
     std::memset(t, 0, sizeof *t);
+    const bool cold = (flags & B200VA_F_COLD) != 0, early = (flags & B200VA_F_INPUTS_STABLE) != 0;
+    t->early_loads = early ? 1 : 0;      // vec kernels only; K0 / K2 ignore it
     switch (variant) {
         case B200VA_K0_SCALAR:
             t->kind = B200VA_K0_SCALAR;
@@ -277,17 +288,22 @@ void default_tune(int variant, size_t n, b200va_tune_t* t)
             break;
     }
     // B200VA_K_AUTO
+    t->kind = B200VA_K1_VEC128;
     t->unroll = 1;
     if (n >= (size_t{1} << 25)) {
-        t->kind = B200VA_K1_VEC128; t->threads = 512; t->ld_hint = LD_PLAIN; t->st_hint = ST_NA;
+        t->threads = 512; t->ld_hint = LD_PLAIN; t->st_hint = ST_NA;
+    } else if (cold && n >= (size_t{1} << 21)) {
+        t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
+        if (early) { t->threads = 256; t->unroll = n < (size_t{3} << 20) ? 4 : 1; }
+        else t->threads = n >= (size_t{3} << 22) ? 512 : 256;              // 2^23 and up (from 1.5 x 2^22): 512
     } else if (n > (size_t{1} << 23)) {
-        t->kind = B200VA_K1_VEC128; t->threads = 128; t->unroll = 2; t->ld_hint = LD_NA_EF; t->st_hint = ST_PLAIN;
+        t->threads = 128; t->unroll = 2; t->ld_hint = LD_NA_EF; t->st_hint = ST_PLAIN;
     } else if (n >= (size_t{1} << 21)) {
-        t->kind = B200VA_K1_VEC128; t->threads = 256; t->unroll = 2; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
+        t->threads = 256; t->unroll = 2; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
     } else if (n >= (size_t{1} << 19)) {
-        t->kind = B200VA_K1_VEC128; t->threads = 512; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
+        t->threads = 512; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
     } else {
-        t->kind = B200VA_K1_VEC128; t->threads = 128; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
+        t->threads = 128; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
     }
 }
 
@@ -616,6 +632,14 @@ int b200va_resolve(int variant, size_t n, b200va_tune_t* out)
     return B200VA_OK;
 }
 
+int b200va_resolve_ex(int variant, size_t n, unsigned flags, b200va_tune_t* out)
+{
+    if (!out || variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
+    if (flags & ~(B200VA_F_INPUTS_STABLE | B200VA_F_COLD)) return B200VA_ERR_INVALID;
+    default_tune(variant, n, out, flags);
+    return B200VA_OK;
+}
+
 int b200va_geometry(const b200va_tune_t* tune, size_t n, int device, unsigned* grid, unsigned* block,
                     unsigned* dyn_smem_bytes)
 {
@@ -642,10 +666,9 @@ int b200va_add_f32(const float* dA, const float* dB, float* dC, size_t n, int va
 int b200va_add_f32_ex(const float* dA, const float* dB, float* dC, size_t n, int variant, unsigned flags, void* stream)
 {
     if (variant < B200VA_K_AUTO || variant > B200VA_K3_VEC256) return B200VA_ERR_VARIANT;
-    if (flags & ~B200VA_F_INPUTS_STABLE) return B200VA_ERR_INVALID;
+    if (flags & ~(B200VA_F_INPUTS_STABLE | B200VA_F_COLD)) return B200VA_ERR_INVALID;
     b200va_tune_t t;
-    default_tune(variant, n, &t);
-    t.early_loads = (flags & B200VA_F_INPUTS_STABLE) ? 1 : 0;   // vec kernels only; ignored by K0/K2
+    default_tune(variant, n, &t, flags);
     return launch(dA, dB, dC, n, t, static_cast<cudaStream_t>(stream));
 }
 
@@ -1282,7 +1305,7 @@ static int stage_slots(b200va_stager* s, const float* hA, const float* hB, float
         float* dC = dB + s->chunk;
         CU_TRY(cudaMemcpyAsync(dA, hA + off, m * sizeof(float), cudaMemcpyHostToDevice, s->slot[i]));
         CU_TRY(cudaMemcpyAsync(dB, hB + off, m * sizeof(float), cudaMemcpyHostToDevice, s->slot[i]));
-        default_tune(variant, m, &t);
+        default_tune(variant, m, &t, B200VA_F_COLD);      // a chunk fresh off the copy engine is never in L2
         RC_TRY(launch(dA, dB, dC, m, t, s->slot[i]));
         CU_TRY(cudaMemcpyAsync(hC + off, dC, m * sizeof(float), cudaMemcpyDeviceToHost, s->slot[i]));
     }
@@ -1322,7 +1345,7 @@ static int stage_lanes(b200va_stager* s, const float* hA, const float* hB, float
         CU_TRY(cudaMemcpyAsync(dB, hB + off, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
         CU_TRY(cudaEventRecord(s->ev_in[i], s->lane_h2d));
         CU_TRY(cudaStreamWaitEvent(s->lane_k, s->ev_in[i], 0));
-        default_tune(variant, m, &t);
+        default_tune(variant, m, &t, B200VA_F_COLD);      // a chunk fresh off the copy engine is never in L2
         RC_TRY(launch(dA, dB, dC, m, t, s->lane_k));
         CU_TRY(cudaEventRecord(s->ev_sum[i], s->lane_k));
         CU_TRY(cudaStreamWaitEvent(s->lane_d2h, s->ev_sum[i], 0));
@@ -1372,7 +1395,7 @@ static int stage_bounce(b200va_stager* s, const float* hA, const float* hB, floa
             CU_TRY(cudaMemcpyAsync(dA + s->chunk, pA + bc, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
             CU_TRY(cudaEventRecord(s->ev_in[i], s->lane_h2d));
             CU_TRY(cudaStreamWaitEvent(s->lane_k, s->ev_in[i], 0));
-            default_tune(variant, m, &t);
+            default_tune(variant, m, &t, B200VA_F_COLD);
             RC_TRY(launch(dA, dA + s->chunk, dA + 2 * s->chunk, m, t, s->lane_k));
             CU_TRY(cudaEventRecord(s->ev_sum[i], s->lane_k));
             CU_TRY(cudaStreamWaitEvent(s->lane_d2h, s->ev_sum[i], 0));

@@ -5,7 +5,7 @@
 //   hot    the same three buffers every launch (for 12*N <= L2 this is an L2 number,
 //          flagged "l2_resident": true -- NOT an HBM figure)
 //   cold   rotating through enough buffer sets that the footprint is >= 4x L2, so every
-//          launch streams from HBM
+//          launch streams from HBM (launched with B200VA_F_COLD: the cold-tuned AUTO class)
 //   cold_chain  the cold rotation launched with B200VA_F_INPUTS_STABLE (consecutive launches never
 //          write each other's inputs): loads run ahead of the programmatic dependency, so the
 //          next launch's DRAM ramp overlaps the previous launch's tail
@@ -105,9 +105,9 @@ int main(int argc, char** argv)
         };
 
         const double hot = time_batches([&] { for (int i = 0; i < iters; ++i) VA(b200va_add_f32(A(0), B(0), C(0), n, variant, st)); });
-        const double cold = sets > 1 ? time_batches([&] { for (int i = 0; i < iters; ++i) { const int s = i % sets; VA(b200va_add_f32(A(s), B(s), C(s), n, variant, st)); } })
+        const double cold = sets > 1 ? time_batches([&] { for (int i = 0; i < iters; ++i) { const int s = i % sets; VA(b200va_add_f32_ex(A(s), B(s), C(s), n, variant, B200VA_F_COLD, st)); } })
                                      : hot;
-        const double cold_chain = time_batches([&] { for (int i = 0; i < iters; ++i) { const int s = sets > 1 ? i % sets : 0; VA(b200va_add_f32_ex(A(s), B(s), C(s), n, variant, B200VA_F_INPUTS_STABLE, st)); } });
+        const double cold_chain = time_batches([&] { for (int i = 0; i < iters; ++i) { const int s = sets > 1 ? i % sets : 0; VA(b200va_add_f32_ex(A(s), B(s), C(s), n, variant, B200VA_F_COLD | B200VA_F_INPUTS_STABLE, st)); } });
         b200va_loop_t* loop = nullptr;
         VA(b200va_loop_create(&loop, A(0), B(0), C(0), n, variant, 100));
         const double graph = time_batches([&] { VA(b200va_loop_run(loop, iters, st)); });

@@ -46,10 +46,10 @@ def _stream_ptr(stream) -> int:
 
 
 def add(a, b, out=None, *, variant=K_AUTO, tune: Tune | None = None, stream=None, inputs_stable: bool = False,
-        full_matrix: bool = False):
+        cold: bool = False, full_matrix: bool = False):
     """C = A + B on the current CUDA stream (asynchronous). ``out`` may be ``a`` or ``b``.
     ``inputs_stable``: b200va_add_f32_ex with B200VA_F_INPUTS_STABLE (the previous launch on the
-    stream does not write a or b).  ``full_matrix``: send an explicit ``tune`` to
+    stream does not write a or b); ``cold``: B200VA_F_COLD (operands not in L2).  ``full_matrix``: send an explicit ``tune`` to
     libb200va_tune.so, which carries every geometry (the production library refuses the
     ones AUTO never picks with ERR_VARIANT)."""
     torch = _torch()
@@ -64,9 +64,9 @@ def add(a, b, out=None, *, variant=K_AUTO, tune: Tune | None = None, stream=None
         if tune is not None:
             h = capi.tune_lib() if full_matrix else lib
             check(h.b200va_add_f32_tuned(pa, pb, pc, a.numel(), C.byref(tune), _stream_ptr(stream)), "b200va_add_f32_tuned")
-        elif inputs_stable:
-            check(lib.b200va_add_f32_ex(pa, pb, pc, a.numel(), _variant(variant), capi.F_INPUTS_STABLE, _stream_ptr(stream)),
-                  "b200va_add_f32_ex")
+        elif inputs_stable or cold:
+            flags = (capi.F_INPUTS_STABLE if inputs_stable else 0) | (capi.F_COLD if cold else 0)
+            check(lib.b200va_add_f32_ex(pa, pb, pc, a.numel(), _variant(variant), flags, _stream_ptr(stream)), "b200va_add_f32_ex")
         else:
             check(lib.b200va_add_f32(pa, pb, pc, a.numel(), _variant(variant), _stream_ptr(stream)), "b200va_add_f32")
     return out

@@ -131,10 +131,12 @@ def test_kernel_names_key_the_ncu_table():
     name what the resolved geometry launches, and an unknown kernel must yield no traffic figure."""
     import bench
 
-    t = pkg.resolve(capi.K_AUTO, 1 << 28)
-    assert t.kernel_name() == "vadd_vec<4,1,0,1,0>"
-    t.early_loads = 1
-    assert t.kernel_name() == "vadd_vec<4,1,0,1,1>"
+    assert pkg.resolve(capi.K_AUTO, 1 << 28).kernel_name() == "vadd_vec<4,1,0,1,0>"
+    assert pkg.resolve(capi.K_AUTO, 1 << 28, capi.F_INPUTS_STABLE).kernel_name() == "vadd_vec<4,1,0,1,1>"
+    assert pkg.resolve(capi.K_AUTO, 1 << 24, capi.F_COLD).kernel_name() == "vadd_vec<4,1,0,0,0>"           # cold-tuned class
+    assert pkg.resolve(capi.K_AUTO, 1 << 21, capi.F_COLD | capi.F_INPUTS_STABLE).kernel_name() == "vadd_vec<4,4,0,0,1>"
+    with pytest.raises(pkg.B200VAError):
+        pkg.resolve(capi.K_AUTO, 1 << 20, 0x40)
     assert pkg.resolve(capi.K_AUTO, 1 << 24).kernel_name() == "vadd_vec<4,2,3,0,0>"
     assert pkg.resolve(capi.K2_TMA, 1 << 28).kernel_name() == "vadd_tma_clc<0,1>"
     assert pkg.resolve(capi.K3_VEC256, 1 << 28).kernel_name() == "vadd_vec<8,1,0,1,0>"

@@ -67,7 +67,9 @@ def test_stager_register_once_on_plain_malloced_arrays():
         for m in (n, n - 7, 1 << 20):                         # sub-ranges of the cached registrations
             hc.fill(-1.0)
             st.add(ha[:m], hb[:m], hc[:m], mode=capi.STAGE_AUTO)
-            assert st.last_mode == capi.STAGE_REGISTER
+            assert st.last_mode == capi.STAGE_LANES             # now page-locked: AUTO sees pinned memory, nothing to register
+            st.add(ha[:m], hb[:m], hc[:m], mode=capi.STAGE_REGISTER)
+            assert st.last_mode == capi.STAGE_REGISTER          # explicit mode 4: cache hit, same pipeline
             assert oracle.first_mismatch(hc[:m].copy(), want[:m].copy()) == -1 and (hc[m:] == -1.0).all()
         # a pinned array is recognised as such (no double registration), tiny arrays take the bounce ring
         pc = torch.empty(n, dtype=torch.float32).pin_memory()

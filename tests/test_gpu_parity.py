@@ -209,11 +209,10 @@ def test_production_library_carries_the_production_set_only():
     ha, hb = oracle.fill_ctr(n, 0x0A), oracle.fill_ctr(n, 0x0B)
     want = oracle.vadd(ha, hb)
     a, b = dev(ha), dev(hb)
-    for size in (1 << 10, 1 << 20, 1 << 22, 1 << 24, 1 << 28):
+    for size in (1 << 10, 1 << 20, 1 << 21, 1 << 22, 1 << 23, 1 << 24, 1 << 28):
         for v in pkg.VARIANTS.values():
-            t = pkg.resolve(v, size)                      # the geometry of that size class, run on our n
-            for early in (0, 1):
-                t.early_loads = early
+            for flags in (0, capi.F_INPUTS_STABLE, capi.F_COLD, capi.F_COLD | capi.F_INPUTS_STABLE):
+                t = pkg.resolve(v, size, flags)           # the geometry of that size class and hint, run on our n
                 out = torch.full((n,), -1.0, dtype=torch.float32, device="cuda")
                 va.add(a, b, out, tune=t)
                 assert_bits_equal(out, want, str(t.as_dict()))
@@ -256,6 +255,12 @@ def test_early_loads_chain_of_launches_is_bit_exact():
         for _ in range(30):
             va.add(A[0], B[0], Cs[1], variant=variant, inputs_stable=True)
         assert va.verify(A[0], B[0], Cs[1]) == (0, -1)
+        # the cold-data hint only changes the geometry AUTO picks, never the bits
+        for i in range(12):
+            s = i % sets
+            va.add(A[s], B[s], Cs[s], variant=variant, inputs_stable=bool(i & 1), cold=True)
+        for s in range(sets):
+            assert va.verify(A[s], B[s], Cs[s]) == (0, -1), (variant, s)
     # write-after-write order on C is kept: the later launch's values must win
     for _ in range(20):
         va.add(A[0], B[0], Cs[0], inputs_stable=True)

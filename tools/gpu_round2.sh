@@ -23,7 +23,7 @@ if has smoke; then
 fi
 
 if has tests; then
-  timeout 1500 python -m pytest tests -q -m gpu -x > "$OUT/pytest_gpu.log" 2>&1; note "pytest gpu exit=$?"
+  timeout 1500 python -m pytest tests -q -m gpu > "$OUT/pytest_gpu.log" 2>&1; note "pytest gpu exit=$?"
   tail -5 "$OUT/pytest_gpu.log"
 fi
 
@@ -44,6 +44,15 @@ if has cold; then
     reps=400; [ $lg -ge 23 ] && reps=200
     timeout 900 $PKG/b200va_tune --n $((1<<lg)) --reps $reps --warmup 20 --rounds 7 --cold < "$OUT/cold_geometries.txt" > "$OUT/cold_2p$lg.jsonl" 2> "$OUT/cold_2p$lg.err"
     note "cold A/B 2^$lg exit=$?"
+  done
+fi
+
+if has hotab; then
+  # the a1 loop's shape: the same buffers relaunched (L2-assisted at these sizes), with and without early loads
+  python tools/gen_ab.py cold > "$OUT/cold_geometries.txt"
+  for lg in ${HOT_SIZES:-22 23 24}; do
+    timeout 600 $PKG/b200va_tune --n $((1<<lg)) --reps 200 --warmup 20 --rounds 7 < "$OUT/cold_geometries.txt" > "$OUT/hot_2p$lg.jsonl" 2> "$OUT/hot_2p$lg.err"
+    note "hot A/B 2^$lg exit=$?"
   done
 fi
 
