@@ -236,11 +236,13 @@ int ensure_smem_optin(tma_fn fn, int device, int bytes)
 // Production choices per size class.  K_AUTO is always the 128-bit kernel; thread count / unroll /
 // cache hints follow the footprint AND what the caller says about the data:
 //
-//  default (the same buffers may be launched again: the a1 loop; profiles/r01/{b,c}_ab_2p*.jsonl, hot A/B)
-//   n >= 2^25       HBM streaming         512 thr x1, stores skip L1            7.23 TB/s @2^28, 7.14 @2^26, 7.00 @2^25
-//   2^23 < n < 2^25 footprint ~ 1-3 x L2  128 thr x2, L2 evict-first loads      7.33 TB/s @2^24 (7.47 with early loads)
-//   2^21..2^23      L2-resident           256 thr x2, plain hints (L2 keeps it) 11.7 TB/s @2^22 (an L2 number)
-//   n < 2^21        launch-bound          512 thr (>= 2^19) / 128 thr, x1
+//  default (the same buffers may be launched again: the a1 loop; hot A/B in profiles/r01/{b,c}_ab_2p*.jsonl and
+//  profiles/r02/b_hot_2p*.jsonl -- at these footprints the numbers are L2-assisted, not HBM figures)
+//   n >= 2^25         HBM streaming         512 thr x1, stores skip L1            7.23 TB/s @2^28, 7.14 @2^26, 7.00 @2^25
+//   2^23 < n < 2^25   footprint 1-3 x L2    128 thr x2, L2 evict-first loads      7.34 TB/s @2^24 (7.46 with early loads)
+//   6 Mi <= n <= 2^23 footprint ~ L2        256 thr x2, stores skip L1            11.6 TB/s @2^23 (plain stores: 8.7); early: x4, 14.3
+//   2^21 <= n < 6 Mi  L2-resident           256 thr x2, plain hints (L2 keeps it) 11.7 TB/s @2^22; early: x4, 13.2
+//   n < 2^21          launch-bound          512 thr (>= 2^19) / 128 thr, x1
 //
 //  B200VA_F_COLD (operands not in L2: the stager's chunks, rotating buffers; profiles/r02/cold_2p*.jsonl,
 //  A/B on >= 4 x L2 of rotating buffer sets) -- one vector per thread wins, the evict-first policy and x2 lose:
@@ -299,7 +301,8 @@ void default_tune(int variant, size_t n, b200va_tune_t* t, unsigned flags = 0)
     } else if (n > (size_t{1} << 23)) {
         t->threads = 128; t->unroll = 2; t->ld_hint = LD_NA_EF; t->st_hint = ST_PLAIN;
     } else if (n >= (size_t{1} << 21)) {
-        t->threads = 256; t->unroll = 2; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
+        t->threads = 256; t->unroll = early ? 4 : 2; t->ld_hint = LD_PLAIN;
+        t->st_hint = n >= (size_t{3} << 21) ? ST_NA : ST_PLAIN;            // from 6 Mi elements the output no longer fits next to the inputs
     } else if (n >= (size_t{1} << 19)) {
         t->threads = 512; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
     } else {
@@ -494,7 +497,7 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
     const int early = (t.early_loads && !aliased) ? 1 : 0;
     vec_fn fn = pick_vec(vw, t.unroll, t.ld_hint, t.st_hint, early, t.scheduler);
     if (!fn) return B200VA_ERR_VARIANT;
-    if (g.block > 512) RC_TRY(check_block_size(fn, g.block));   // deep unrolls: the CTA size is register-limited
+    if (g.block > 256) RC_TRY(check_block_size(fn, g.block));   // deep unrolls: the CTA size is register-limited
     return launch_kernel(fn, g.grid, g.block, 0, stream, dA, dB, dC, n, head, nvec, g.ntiles);
 }
 
@@ -1316,6 +1319,16 @@ static int stage_slots(b200va_stager* s, const float* hA, const float* hB, float
     return B200VA_OK;
 }
 
+// Fault injection for the error-path test (tests/test_gpu_host_path.py): with
+// B200VA_TEST_FAIL_CHUNK=k in the environment the lanes pipeline fails ONCE per process, right
+// after it has queued chunk k's H2D copies -- i.e. with DMA in flight on the caller's arrays.
+static bool inject_fault_at_chunk(size_t k)
+{
+    static const long at = [] { const char* e = std::getenv("B200VA_TEST_FAIL_CHUNK"); return e ? std::atol(e) : -1L; }();
+    static std::atomic<bool> fired{false};
+    return at >= 0 && static_cast<long>(k) == at && !fired.exchange(true);
+}
+
 static int stage_lanes(b200va_stager* s, const float* hA, const float* hB, float* hC, size_t n, int variant)
 {
     // lanes: every H2D copy queues on one stream, every add on a second, every D2H on a
@@ -1344,6 +1357,7 @@ static int stage_lanes(b200va_stager* s, const float* hA, const float* hB, float
         CU_TRY(cudaMemcpyAsync(dA, hA + off, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
         CU_TRY(cudaMemcpyAsync(dB, hB + off, m * sizeof(float), cudaMemcpyHostToDevice, s->lane_h2d));
         CU_TRY(cudaEventRecord(s->ev_in[i], s->lane_h2d));
+        if (inject_fault_at_chunk(k)) return B200VA_ERR_INVALID;   // test hook: fail with copies in flight
         CU_TRY(cudaStreamWaitEvent(s->lane_k, s->ev_in[i], 0));
         default_tune(variant, m, &t, B200VA_F_COLD);      // a chunk fresh off the copy engine is never in L2
         RC_TRY(launch(dA, dB, dC, m, t, s->lane_k));

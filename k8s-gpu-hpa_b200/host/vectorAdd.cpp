@@ -422,7 +422,9 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
     const size_t m = e - b;
     bool ok = true;
     auto CK = [&](cudaError_t err, const char* what) { if (ok && err != cudaSuccess) { fail(what, cudaGetErrorString(err)); ok = false; } };
-    auto VA = [&](int rc, const char* what) { if (ok && rc != B200VA_OK) { fail(what, b200va_strerror(rc)); ok = false; } };
+    auto VA = [&](int rc, const char* what) {
+        if (ok && rc != B200VA_OK) { fail(what, (std::string(b200va_strerror(rc)) + " [" + std::to_string(rc) + "]").c_str()); ok = false; }
+    };
 
     CK(cudaSetDevice(rank), "select device");
     float *dA = nullptr, *dB = nullptr, *dC = nullptr, *hA = nullptr, *hB = nullptr, *hC = nullptr;

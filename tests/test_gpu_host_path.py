@@ -124,18 +124,44 @@ def test_stager_restores_the_callers_current_device():
 
 
 def test_stager_error_in_the_middle_leaves_nothing_in_flight():
-    """A failing call (zero-copy mode on pageable arrays: the runtime refuses the pointer) returns an
-    error code, and the stager is usable right after -- nothing is still running on its streams."""
-    n = 1 << 22
-    ha, hb = oracle.fill_ctr(n, 0x0A), oracle.fill_ctr(n, 0x0B)
-    hc = np.empty_like(ha)
-    with va.Stager(0, 1 << 20, 3) as st:
-        with pytest.raises(capi.B200VAError):
-            st.add(ha, hb, hc, mode=capi.STAGE_ZEROCOPY)
-        st.add(ha, hb, hc, mode=capi.STAGE_BOUNCE)
-        assert oracle.first_mismatch(hc, oracle.vadd(ha, hb)) == -1
-    x = torch.ones(16, device="cuda")
-    assert float(va.add(x, x).sum()) == 32.0                 # no latched CUDA error either
+    """A failure in the middle of the pipeline (injected right after chunk 1's H2D copies were
+    queued) returns an error code only after every stream of the stager has drained: the caller
+    may overwrite or free its arrays at once, and the stager works on the next call."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+
+    from conftest import ROOT
+
+    code = textwrap.dedent("""
+        import numpy as np, torch, oracle
+        from k8s_gpu_hpa_b200 import capi, vector_add as va
+        n = 6 * (1 << 20) + 11
+        ha = torch.from_numpy(oracle.fill_ctr(n, 0x0A)).pin_memory()
+        hb = torch.from_numpy(oracle.fill_ctr(n, 0x0B)).pin_memory()
+        hc = torch.full((n,), -1.0).pin_memory()
+        want = oracle.vadd(ha.numpy(), hb.numpy())
+        with va.Stager(0, 1 << 20, 3) as st:
+            try:
+                st.add(ha, hb, hc, mode=capi.STAGE_LANES)
+                raise SystemExit("the injected fault did not surface")
+            except capi.B200VAError as e:
+                assert e.code == capi.ERR_INVALID, e
+            # drained: chunk 0 completed (its D2H landed), nothing of chunk 2.. was ever started
+            got = hc.numpy()
+            assert oracle.first_mismatch(got[:1 << 20].copy(), want[:1 << 20].copy()) == -1
+            assert (got[2 << 20:] == -1.0).all()
+            ha.zero_(); ha.copy_(torch.from_numpy(oracle.fill_ctr(n, 0x0A)))   # scribbling over A right away is safe
+            st.add(ha, hb, hc, mode=capi.STAGE_LANES)                           # the hook fires once: this call is clean
+            assert oracle.first_mismatch(hc.numpy(), want) == -1
+        x = torch.ones(16, device="cuda")
+        assert float(va.add(x, x).sum()) == 32.0                                 # no latched CUDA error either
+        print("OK")
+    """)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, B200VA_TEST_FAIL_CHUNK="1", PYTHONPATH=ROOT))
+    assert p.returncode == 0 and "OK" in p.stdout, p.stdout + p.stderr
 
 
 def test_cli_zero_arguments_is_the_reference_process():

@@ -197,7 +197,13 @@ def test_tuned_geometries_are_all_bit_exact():
             torch.cuda.synchronize()
             assert_bits_equal(out, want, "after refused launch")
             continue
-        va.add(a, b, out, tune=t, full_matrix=True)
+        try:
+            va.add(a, b, out, tune=t, full_matrix=True)
+        except pkg.B200VAError as e:
+            # register-limited CTA sizes are refused up front (ERR_VARIANT), never fail at launch
+            live = t.threads * t.unroll * (2 if t.kind == capi.K3_VEC256 else 1)
+            assert e.code == capi.ERR_VARIANT and t.kind in (capi.K1_VEC128, capi.K3_VEC256) and live >= 8192, t.as_dict()
+            continue
         torch.cuda.synchronize()
         assert_bits_equal(out, want, str(t.as_dict()))
 
