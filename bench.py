@@ -194,6 +194,34 @@ def device_for_rank(local_rank: int, ws: int, ndev: int, numa_of) -> tuple[int, 
     return order[local_rank], nodes
 
 
+class bound_to_node:
+    """Runs the calling thread on the CPUs of one NUMA node for the duration of the block, so that
+    pages it first-touches land on that node (what `numactl --cpunodebind` gives a process whose
+    GPU hangs off that socket).  No-op when the node or its CPU list is unknown."""
+
+    def __init__(self, node: int):
+        self.node, self.old = node, None
+
+    def __enter__(self):
+        try:
+            text = open(f"/sys/devices/system/node/node{self.node}/cpulist").read().strip()
+            cpus = set()
+            for part in text.split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            old = os.sched_getaffinity(0)
+            if cpus & old:
+                os.sched_setaffinity(0, cpus & old)
+                self.old = old
+        except Exception:
+            self.old = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            os.sched_setaffinity(0, self.old)
+
+
 def time_steps(fn, steps: int, stream, sharding, sampler=None):
     """barrier + sync, `steps` calls of fn between two CUDA events on `stream`, sync + barrier;
     returns the MAX over ranks of the elapsed milliseconds."""
@@ -346,8 +374,12 @@ def run_ours(args, emit=print) -> None:
             p.free()
 
         # ---- the same call on the memory the reference's process has: plain malloc'd arrays
-        qa, qb, qc = (torch.empty(n, dtype=torch.float32) for _ in range(3))     # pageable
-        qa.copy_(a); qb.copy_(b); qc.zero_()
+        with bound_to_node(int(capi.lib.b200va_device_numa_node())):             # first touch next to the GPU, like a pod pinned to its socket
+            qa, qb, qc = (torch.empty(n, dtype=torch.float32) for _ in range(3))     # pageable
+            for q in (qa, qb, qc):
+                q.numpy()[::1024] = 0.0          # first touch of every page by THIS (bound) thread, not by an OpenMP pool
+        pageable_nodes = sharding.gather_ints([int(capi.lib.b200va_host_node_of(q.data_ptr())) for q in (qa, qb, qc)])
+        qa.copy_(a); qb.copy_(b)
         torch.cuda.synchronize()
         with va.Stager(dev_index, args.chunk_elems, args.depth) as stg:
             sharding.barrier()
@@ -373,7 +405,7 @@ def run_ours(args, emit=print) -> None:
                         "path": "b200va_stager_add_f32 mode AUTO -> " + {4: "register-once (cudaHostRegister cached by range) + lanes pipeline",
                                                                           3: "pinned bounce ring + copy threads (registration refused)",
                                                                           2: "lanes"}.get(stage_mode, str(stage_mode)),
-                        "stage_mode": stage_mode,
+                        "stage_mode": stage_mode, "numa_A_B_C_per_rank": pageable_nodes,
                         "roofline_frac": probe_ms / (ms_pg / e2e_steps)}
 
     # ---- BASELINE.json configs[4]: the sustained launch loop, N = 2^24, 5000 launches in 50-launch graphs

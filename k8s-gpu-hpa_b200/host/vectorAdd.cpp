@@ -438,16 +438,18 @@ void shard_worker(const Options& o, int rank, Barrier& bar, ShardResult& r, Nvml
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "create stream");
         CK(cudaEventCreate(&e0), "create event"); CK(cudaEventCreate(&e1), "create event");
         CK(cudaMalloc(&dRes, 4 * sizeof(uint64_t)), "allocate result words");
-        if (staged && o.pageable) {
-            // the reference process's own memory: plain malloc (a2); the stager page-locks it on first sight
-            hA = static_cast<float*>(std::malloc(m ? m * 4 : 4));
-            hB = static_cast<float*>(std::malloc(m ? m * 4 : 4));
-            hC = static_cast<float*>(std::malloc(m ? m * 4 : 4));
-            if (!hA || !hB || !hC) { fail("allocate host vectors", "out of memory"); ok = false; }
-        } else if (staged) {
-            VA(b200va_host_alloc(reinterpret_cast<void**>(&hA), m * 4), "allocate pinned A");
-            VA(b200va_host_alloc(reinterpret_cast<void**>(&hB), m * 4), "allocate pinned B");
-            VA(b200va_host_alloc(reinterpret_cast<void**>(&hC), m * 4), "allocate pinned C");
+        if (staged) {
+            if (o.pageable) {
+                // the reference process's own memory: plain malloc (a2); the stager page-locks it on first sight
+                hA = static_cast<float*>(std::malloc(m ? m * 4 : 4));
+                hB = static_cast<float*>(std::malloc(m ? m * 4 : 4));
+                hC = static_cast<float*>(std::malloc(m ? m * 4 : 4));
+                if (!hA || !hB || !hC) { fail("allocate host vectors", "out of memory"); ok = false; }
+            } else {
+                VA(b200va_host_alloc(reinterpret_cast<void**>(&hA), m * 4), "allocate pinned A");
+                VA(b200va_host_alloc(reinterpret_cast<void**>(&hB), m * 4), "allocate pinned B");
+                VA(b200va_host_alloc(reinterpret_cast<void**>(&hC), m * 4), "allocate pinned C");
+            }
             if (ok) parallel_spans(m, std::max(1, host_cpus() / o.gpus), [&](size_t lo, size_t hi) {
                 b200va_host_fill_ctr_f32(hA + lo, hi - lo, o.seed, b + lo);
                 b200va_host_fill_ctr_f32(hB + lo, hi - lo, o.seed + 1, b + lo);
