@@ -23,7 +23,7 @@ if has smoke; then
 fi
 
 if has tests; then
-  timeout 1500 python -m pytest tests -q -m gpu > "$OUT/pytest_gpu.log" 2>&1; note "pytest gpu exit=$?"
+  timeout 1500 python -m pytest tests -q -m gpu ${PYTEST_X:-} > "$OUT/pytest_gpu.log" 2>&1; note "pytest gpu exit=$?"
   tail -5 "$OUT/pytest_gpu.log"
 fi
 
@@ -119,7 +119,7 @@ if has cli; then
   ( cd $PKG
     timeout 600 ./vectorAdd --mode resident --n 2^24 --iters 5000 --graph 50 --json "../$OUT/cli_loop_graph.json" > /dev/null 2>> "../$OUT/cli.err"
     timeout 600 ./vectorAdd --mode resident --n 2^28 --iters 100 --cpu-baseline --json "../$OUT/cli_2p28.json" > /dev/null 2>> "../$OUT/cli.err" )
-  timeout 600 python tools/hpa_trigger_replay.py 12 > "$OUT/hpa_trigger_replay.jsonl" 2> "$OUT/hpa_trigger_replay.err"; note "hpa replay exit=$?"
+  timeout 600 python tools/hpa_trigger_replay.py ${HPA_S:-20} > "$OUT/hpa_trigger_replay.jsonl" 2> "$OUT/hpa_trigger_replay.err"; note "hpa replay exit=$?"
 fi
 
 if has probe; then
