@@ -283,12 +283,12 @@ def cli_strong(gpus: int, cli: str) -> dict:
     with tempfile.TemporaryDirectory() as d:
         out = os.path.join(d, "cli.json")
         try:
-            p = subprocess.run([cli, "--gpus", str(gpus), "--n", "2^30", "--iters", "20", "--json", out],
+            p = subprocess.run([cli, "--mode", "resident", "--gpus", str(gpus), "--n", "2^30", "--iters", "20", "--json", out],
                                capture_output=True, text=True, timeout=300)
             r = json.load(open(out))
         except Exception as e:          # reported, never fatal for the contract line
             return {"error": repr(e)[:200]}
-    return {"command": f"vectorAdd --gpus {gpus} --n 2^30 --iters 20", "exit_code": p.returncode,
+    return {"command": f"vectorAdd --mode resident --gpus {gpus} --n 2^30 --iters 20", "exit_code": p.returncode,
             "value": r["elements_per_s"], "unit": UNIT, "ms_per_step": r["ms_per_pass"], "mismatches": r["mismatches"],
             "frac_of_8TBps_nameplate_per_gpu": r["roofline_frac_of_8TBps_per_gpu"],
             "digest_ok": (int(r["digest_sum"], 16), int(r["digest_xor"], 16)) == DIGEST_2P30}

@@ -103,6 +103,43 @@ def test_stager_register_once_on_plain_malloced_arrays():
             st.add(pa, pb, pc, mode=9)
 
 
+def test_concurrent_callers_on_one_device():
+    """The library is re-entrant: four host threads, each with its own stream and its own stager, call the
+    device entry points and the host-buffer path at the same time on the same GPU (ctypes releases the GIL)."""
+    import threading
+
+    n = 3_000_001
+    errors: list = []
+
+    def worker(k: int):
+        try:
+            torch.cuda.set_device(0)
+            ha, hb = oracle.fill_ctr(n, 0x0A, k * n), oracle.fill_ctr(n, 0x0B, k * n)
+            want = oracle.vadd(ha, hb)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                a, b = torch.from_numpy(ha).cuda(), torch.from_numpy(hb).cuda()
+                for i in range(25):
+                    c = va.add(a, b, variant=("auto", "k2", "k3", "k1")[(i + k) % 4], inputs_stable=bool(i & 1))
+                stream.synchronize()
+                assert oracle.first_mismatch(c.cpu().numpy(), want) == -1
+            hc = np.empty_like(ha)
+            with va.Stager(0, 1 << 19, 2) as st:
+                for mode in (capi.STAGE_BOUNCE, capi.STAGE_AUTO, capi.STAGE_AUTO):
+                    hc.fill(-1.0)
+                    st.add(ha, hb, hc, mode=mode)
+                    assert oracle.first_mismatch(hc, want) == -1
+        except BaseException as e:      # noqa: BLE001 -- reported to the main thread
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_stager_restores_the_callers_current_device():
     """Entry points that take a `device` leave the calling thread on the device it was on."""
     n = 1 << 20
@@ -231,7 +268,9 @@ def test_cli_staged_mode_and_duty_cycle():
     p = va.run_cli("--mode", "staged", "--host-mem", "pageable", "--n", str((1 << 23) + 1), "--iters", "3")
     assert p.returncode == 0, p.stderr
     r = json.loads(p.stdout.strip().splitlines()[-1])
-    assert r["mismatches"] == 0 and r["stage_mode"] == capi.STAGE_REGISTER and r["host_mem"].startswith("pageable")
+    assert r["mismatches"] == 0 and r["host_mem"].startswith("pageable")
+    assert r["first_stage_mode"] == capi.STAGE_REGISTER      # pass 1 page-locked the malloc'd arrays ...
+    assert r["stage_mode"] == capi.STAGE_LANES               # ... so the later passes see pinned memory
     assert r["first_pass_wall_ms"] > 0
     import tempfile
 

@@ -85,3 +85,28 @@ def test_random_tma_geometries(pools, n, threads, stages, tile_k, mode, hint):
     out = va.add(a[:n], b[:n], tune=t, full_matrix=True)
     torch.cuda.synchronize()
     assert oracle.first_mismatch(out.cpu().numpy(), oracle.vadd(ha[:n].copy(), hb[:n].copy())) == -1
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(0, POOL), chunk_log=st.integers(10, 17), depth=st.integers(1, 4), mode=st.sampled_from([-1, 0, 2, 3, 4]),
+       pinned=st.booleans(), off=st.integers(0, 5))
+def test_random_host_path_shapes(pools, n, chunk_log, depth, mode, pinned, off):
+    """The host-buffer path with random lengths, chunk sizes, ring depths, pipelines and host memory kinds
+    (pinned vs plain malloc, misaligned starts): always the oracle's bits, never a byte outside [0, n)."""
+    ha, hb, _, _ = pools
+    n = min(n, POOL - off)
+    a, b = ha[off:off + n], hb[off:off + n]
+    if pinned:
+        a, b = torch.from_numpy(a.copy()).pin_memory(), torch.from_numpy(b.copy()).pin_memory()
+        out = torch.full((n + 8,), -3.0).pin_memory()
+        view, got = out[:n], out.numpy()
+    else:
+        a, b = a.copy(), b.copy()
+        got = np.full(n + 8, -3.0, np.float32)
+        view = got[:n]
+    with va.Stager(0, 1 << chunk_log, depth) as stg:
+        stg.add(a, b, view, mode=mode)
+        stg.add(a, b, view, mode=mode)                      # second call: cached registration / reused ring
+    want = oracle.vadd(ha[off:off + n].copy(), hb[off:off + n].copy())
+    assert oracle.first_mismatch(got[:n].copy(), want) == -1
+    assert (got[n:] == -3.0).all()

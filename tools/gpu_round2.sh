@@ -72,6 +72,24 @@ if has skew; then
   note "channel skew sweep exit=$?"
 fi
 
+if has sanitizer; then
+  # the round-2 kernels under compute-sanitizer: early-load form, K1c (mbarrier + try_cancel response slot), K2c after the edge fix
+  cat > "$OUT/san_geos.txt" <<'GEO'
+2 512 1 0 0 1 0 0 0 1 0
+2 256 4 0 0 0 0 0 0 1 0
+2 256 2 0 0 1 0 0 0 0 1
+2 128 4 0 0 1 0 0 0 1 1
+4 256 2 0 0 1 0 0 0 1 1
+3 128 0 1 0 1 3 8192 2
+GEO
+  for tool in memcheck racecheck synccheck initcheck; do
+    timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 $PKG/b200va_tune --n 300007 --reps 3 --warmup 1 --rounds 1 --cold < "$OUT/san_geos.txt" > "$OUT/sanitizer_$tool.log" 2>&1
+    note "compute-sanitizer $tool exit=$? ($(grep -c 'ERROR SUMMARY: 0 errors' "$OUT/sanitizer_$tool.log") clean summaries)"
+  done
+  timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 $PKG/vectorAdd --mode resident --n 300007 --iters 40 --graph 8 > "$OUT/sanitizer_memcheck_loop.log" 2>&1
+  note "compute-sanitizer memcheck launch loop exit=$?"
+fi
+
 if has nsweep; then
   timeout 900 $PKG/b200va_sweep --lo 16 --hi 30 > "$OUT/sweep_n.jsonl" 2> "$OUT/sweep_n.err"; note "nsweep exit=$?"
 fi
