@@ -81,10 +81,14 @@ typedef struct b200va_tune {
     int tile_bytes;   /* TMA: bytes per array per stage (multiple of 2048)              */
     int store_mode;   /* TMA: 0 = st.global from registers, 1 = bulk store from smem,
                          2 = register stores + cluster-launch-control tile scheduler    */
-    int early_loads;  /* vec: 1 = issue the first tile's loads before the programmatic
-                         dependency on the previous launch resolves (only stores wait).
-                         Requires that the previous launch on the stream does not write A
-                         or B; forced to 0 when C aliases A or B.  See b200va_add_f32_ex. */
+    int early_loads;  /* vec: what a CTA does about its first tile before the programmatic
+                         dependency on the previous launch resolves:
+                         1 = issue the loads themselves (only the stores wait).  Requires that
+                             the previous launch on the stream does not write A or B; replaced
+                             by 2 when C aliases A or B.  See b200va_add_f32_ex.
+                         2 = bulk-prefetch the A and B tiles into L2 (cp.async.bulk.prefetch.L2);
+                             loads and stores wait.  Always legal (L2 is the coherence point);
+                             pays off on data that is not already in L2.                     */
     int scheduler;    /* vec: 0 = hardware block scheduler (one CTA per tile, or the static
                          persistent split of ctas_per_sm), 1 = cluster launch control:
                          resident CTAs cancel and take over not-yet-started ones (K1c)   */
@@ -133,7 +137,10 @@ int b200va_add_f32_tuned(const float *dA, const float *dB, float *dC, size_t n,
 #define B200VA_F_INPUTS_STABLE 1u
 /* B200VA_F_COLD: the operands are not L2-resident (fresh from a copy engine, or one of many
  * buffer sets touched in rotation): B200VA_K_AUTO then resolves to the geometry tuned on
- * rotating buffers instead of the one tuned for relaunching the same buffers.  A hint only. */
+ * rotating buffers instead of the one tuned for relaunching the same buffers -- in particular
+ * the launch prefetches its first tiles into L2 while the previous launch is still draining
+ * (early_loads = 2; no promise about the previous launch is needed for that).  A hint only;
+ * vectors of 2^25 elements and more can never be L2-resident and are always treated as cold. */
 #define B200VA_F_COLD          2u
 int b200va_add_f32_ex(const float *dA, const float *dB, float *dC, size_t n,
                       int variant, unsigned flags, void *stream);

@@ -98,19 +98,41 @@ int current_dev_info(const b200va_devinfo_t** out)
 using vec_fn = void (*)(const float*, const float*, float*, size_t, size_t, size_t, size_t);
 
 template <int VW, int UNROLL, int LD, int ST>
+vec_fn pick_early_hw(int early)
+{
+    switch (early) {
+        case 0: return vadd_vec<VW, UNROLL, LD, ST, 0>;
+        case 1: return vadd_vec<VW, UNROLL, LD, ST, 1>;
+        case 2: return vadd_vec<VW, UNROLL, LD, ST, 2>;
+    }
+    return nullptr;
+}
+
+template <int VW, int UNROLL, int LD, int ST>
+vec_fn pick_early_clc(int early)
+{
+    switch (early) {
+        case 0: return vadd_vec_clc<VW, UNROLL, LD, ST, 0>;
+        case 1: return vadd_vec_clc<VW, UNROLL, LD, ST, 1>;
+        case 2: return vadd_vec_clc<VW, UNROLL, LD, ST, 2>;
+    }
+    return nullptr;
+}
+
+template <int VW, int UNROLL, int LD, int ST>
 vec_fn pick_sched(int early, int sched)
 {
     if (sched == 1) {
 #ifdef B200VA_TUNE_MATRIX
-        return early ? vadd_vec_clc<VW, UNROLL, LD, ST, true> : vadd_vec_clc<VW, UNROLL, LD, ST, false>;
+        return pick_early_clc<VW, UNROLL, LD, ST>(early);
 #else
         if constexpr (VW == 4 && LD == LD_PLAIN && ST == ST_NA && (UNROLL == 2 || UNROLL == 4))
-            return early ? vadd_vec_clc<VW, UNROLL, LD, ST, true> : vadd_vec_clc<VW, UNROLL, LD, ST, false>;
+            return pick_early_clc<VW, UNROLL, LD, ST>(early);
         else
             return nullptr;
 #endif
     }
-    return early ? vadd_vec<VW, UNROLL, LD, ST, true> : vadd_vec<VW, UNROLL, LD, ST, false>;
+    return pick_early_hw<VW, UNROLL, LD, ST>(early);
 }
 
 template <int VW, int UNROLL, int LD>
@@ -244,13 +266,16 @@ int ensure_smem_optin(tma_fn fn, int device, int bytes)
 //   2^21 <= n < 6 Mi  L2-resident           256 thr x2, plain hints (L2 keeps it) 11.7 TB/s @2^22; early: x4, 13.2
 //   n < 2^21          launch-bound          512 thr (>= 2^19) / 128 thr, x1
 //
-//  B200VA_F_COLD (operands not in L2: the stager's chunks, rotating buffers; profiles/r02/cold_2p*.jsonl,
-//  A/B on >= 4 x L2 of rotating buffer sets) -- one vector per thread wins, the evict-first policy and x2 lose:
-//   2^23 <= n < 2^25   512 thr x1   6.42 TB/s @2^23, 6.81 @2^24   (hot-tuned classes: 6.26 / 6.46)
-//   2^21 <= n < 2^23   256 thr x1   4.81 TB/s @2^21, 5.81 @2^22   (4.62 / 5.75)
-//  B200VA_F_COLD | B200VA_F_INPUTS_STABLE (early loads hide the next launch's DRAM ramp behind this one's tail)
-//   2^22 <= n < 2^25   256 thr x1   6.53 TB/s @2^22, 6.94 @2^23, 7.07 @2^24
-//   n < 2^22           256 thr x4   6.90 TB/s @2^21 (twice the bytes in flight per CTA for the short grid)
+//  B200VA_F_COLD (operands not in L2: the stager's chunks, rotating buffers; profiles/r02/{a,g}_cold_2p*.jsonl, A/B on
+//  >= 4 x L2 of rotating buffer sets).  The launch boundary is what costs here (~1.8 us: the previous grid's tail, then a
+//  full DRAM round trip before the first store), and the always-legal L2 bulk prefetch ahead of griddepcontrol.wait
+//  (early_loads = 2) recovers it without any promise from the caller:
+//   n >= 12 Mi         512 thr x1   7.08 TB/s @2^24          (r01 hot-tuned class: 6.46; plain 512 x1: 6.81)
+//   3 Mi <= n < 12 Mi  512 thr x2   6.95 @2^22, 7.06 @2^23   (5.75 / 6.26; plain 256/512 x1: 5.83 / 6.45)
+//   n < 3 Mi           256 thr x1   4.49 @2^20, 5.87 @2^21   (3.50 / 4.62)
+//  B200VA_F_COLD | B200VA_F_INPUTS_STABLE: from 3 Mi the prefetch form is already the best; below, register loads
+//  ahead of the wait (early_loads = 1) are: 256 thr x4 6.91 TB/s @2^21, 128 thr x2 6.67 @2^20.
+//  n >= 2^25 is never L2-resident, so it always takes the prefetch form (7.25 vs 7.20 TB/s @2^27, 7.22 vs 7.20 @2^28).
 void default_tune(int variant, size_t n, b200va_tune_t* t, unsigned flags = 0)
 {
     std::memset(t, 0, sizeof *t);
@@ -292,18 +317,28 @@ void default_tune(int variant, size_t n, b200va_tune_t* t, unsigned flags = 0)
     // B200VA_K_AUTO
     t->kind = B200VA_K1_VEC128;
     t->unroll = 1;
-    if (n >= (size_t{1} << 25)) {
+    const size_t Mi = size_t{1} << 20;
+    if (n >= 32 * Mi) {
         t->threads = 512; t->ld_hint = LD_PLAIN; t->st_hint = ST_NA;
-    } else if (cold && n >= (size_t{1} << 21)) {
+        if (!early) t->early_loads = 2;
+    } else if (cold) {
         t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
-        if (early) { t->threads = 256; t->unroll = n < (size_t{3} << 20) ? 4 : 1; }
-        else t->threads = n >= (size_t{3} << 22) ? 512 : 256;              // 2^23 and up (from 1.5 x 2^22): 512
-    } else if (n > (size_t{1} << 23)) {
+        if (early && n < 3 * Mi) {                       // launch-latency dominated: register loads ahead of the wait
+            if (n >= 3 * Mi / 2) { t->threads = 256; t->unroll = 4; }
+            else if (n >= Mi / 2) { t->threads = 128; t->unroll = 2; }
+            else t->threads = 128;
+        } else {                                          // L2 bulk prefetch ahead of the wait
+            t->early_loads = 2;
+            if (n >= 12 * Mi) t->threads = 512;
+            else if (n >= 3 * Mi) { t->threads = 512; t->unroll = 2; }
+            else t->threads = n >= Mi / 2 ? 256 : 128;
+        }
+    } else if (n > 8 * Mi) {
         t->threads = 128; t->unroll = 2; t->ld_hint = LD_NA_EF; t->st_hint = ST_PLAIN;
-    } else if (n >= (size_t{1} << 21)) {
+    } else if (n >= 2 * Mi) {
         t->threads = 256; t->unroll = early ? 4 : 2; t->ld_hint = LD_PLAIN;
-        t->st_hint = n >= (size_t{3} << 21) ? ST_NA : ST_PLAIN;            // from 6 Mi elements the output no longer fits next to the inputs
-    } else if (n >= (size_t{1} << 19)) {
+        t->st_hint = n >= 6 * Mi ? ST_NA : ST_PLAIN;            // from 6 Mi elements the output no longer fits next to the inputs
+    } else if (n >= Mi / 2) {
         t->threads = 512; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
     } else {
         t->threads = 128; t->ld_hint = LD_PLAIN; t->st_hint = ST_PLAIN;
@@ -493,8 +528,9 @@ int launch(const float* dA, const float* dB, float* dC, size_t n, b200va_tune_t 
         return launch_kernel(fn, g.grid, g.block, g.smem, stream, dA, dB, dC, n, head, nvec,
                              static_cast<uint32_t>(t.tile_bytes), static_cast<uint32_t>(t.stages));
     }
-    // early loads read A and B while the previous launch may still be running: never when C aliases an input
-    const int early = (t.early_loads && !aliased) ? 1 : 0;
+    // early register loads (1) read A and B while the previous launch may still be running: never when C aliases
+    // an input -- the always-legal L2 prefetch (2) takes their place
+    const int early = (t.early_loads == 1 && aliased) ? 2 : t.early_loads;
     vec_fn fn = pick_vec(vw, t.unroll, t.ld_hint, t.st_hint, early, t.scheduler);
     if (!fn) return B200VA_ERR_VARIANT;
     if (g.block > 256) RC_TRY(check_block_size(fn, g.block));   // deep unrolls: the CTA size is register-limited
@@ -691,7 +727,7 @@ int b200va_add_f32_tuned(const float* dA, const float* dB, float* dC, size_t n,
     if (t.unroll == 0) t.unroll = d.unroll ? d.unroll : 1;
     if (t.stages == 0) t.stages = d.stages;
     if (t.tile_bytes == 0) t.tile_bytes = d.tile_bytes;
-    if ((t.early_loads | t.scheduler) & ~1) return B200VA_ERR_VARIANT;
+    if (t.early_loads < 0 || t.early_loads > 2 || (t.scheduler & ~1)) return B200VA_ERR_VARIANT;
     return launch(dA, dB, dC, n, t, static_cast<cudaStream_t>(stream));
 }
 

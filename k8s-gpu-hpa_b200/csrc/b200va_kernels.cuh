@@ -16,12 +16,16 @@
 //   K1c vadd_vec_clc     the K1/K3 tile body with Blackwell's cluster-launch-control
 //                        scheduler: resident CTAs cancel not-yet-started CTAs of the grid
 //                        and take over their tiles (no CTA relaunch per tile).
-//   EARLY (K1/K3/K1c)    the loads of a CTA's first tile are issued BEFORE the programmatic
-//                        dependency on the previous launch resolves (griddepcontrol.wait);
-//                        only the stores wait.  Legal when the previous launch on the
-//                        stream does not write A or B (the launch loop, a1: the previous
-//                        launch is the same add, which writes only C) -- it overlaps this
-//                        launch's DRAM ramp with the previous launch's tail.
+//   EARLY (K1/K3/K1c)    what a CTA does about its first tile BEFORE the programmatic dependency
+//                        on the previous launch resolves (griddepcontrol.wait):
+//                        1  issues the loads themselves; only the stores wait.  Legal when the
+//                           previous launch on the stream does not write A or B (the launch
+//                           loop, a1: the previous launch is the same add, which writes only C).
+//                        2  one thread bulk-prefetches the A and B tiles into L2
+//                           (cp.async.bulk.prefetch.L2), loads and stores wait.  ALWAYS legal:
+//                           L2 is the coherence point, a line prefetched early and then written
+//                           by the previous launch is simply up to date when it is read.
+//                        Both overlap this launch's DRAM ramp with the previous launch's tail.
 //   K2  vadd_tma         persistent CTAs; one producer lane issues 1-D cp.async.bulk
 //                        copies of an A tile and a B tile into a `stages`-deep smem ring
 //                        (mbarrier complete_tx); consumer warps add from smem and either
@@ -154,7 +158,20 @@ __device__ __forceinline__ void vec_tile(const float* a, const float* b, float* 
     }
 }
 
-template <int VW, int UNROLL, int LD, int ST, bool EARLY>
+// EARLY == 2: thread 0 asks the L2 to fetch the CTA's first A and B tiles (two bulk-prefetch
+// instructions) while the previous launch is still draining.
+template <int VW>
+__device__ __forceinline__ void prefetch_first_tile(const float* a, const float* b, size_t tile, size_t tile_vecs, size_t nvec)
+{
+    if (threadIdx.x != 0 || tile * tile_vecs >= nvec) return;
+    const size_t v0 = tile * tile_vecs;
+    const size_t nv = nvec - v0 < tile_vecs ? nvec - v0 : tile_vecs;
+    const uint32_t bytes = static_cast<uint32_t>(nv * VW * sizeof(float));      // a multiple of 16, <= 256 KiB
+    bulk_prefetch_l2(a + v0 * VW, bytes);
+    bulk_prefetch_l2(b + v0 * VW, bytes);
+}
+
+template <int VW, int UNROLL, int LD, int ST, int EARLY>
 __global__ void vadd_vec(const float* A, const float* B, float* C, size_t n, size_t head,
                          size_t nvec, size_t ntiles)
 {
@@ -166,8 +183,9 @@ __global__ void vadd_vec(const float* A, const float* B, float* C, size_t n, siz
     float* c = C + head;
     const size_t tile_vecs = static_cast<size_t>(blockDim.x) * UNROLL;
     pdl_launch_dependents();
-    bool waited = !EARLY;
-    if constexpr (!EARLY) pdl_wait();   // everything above overlapped the previous launch's tail
+    if constexpr (EARLY == 2) prefetch_first_tile<VW>(a, b, blockIdx.x, tile_vecs, nvec);
+    bool waited = EARLY != 1;
+    if constexpr (EARLY != 1) pdl_wait();   // everything above overlapped the previous launch's tail
 
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
         vec_tile<VW, UNROLL, LD, ST>(a, b, c, tile, tile_vecs, nvec, pol, waited);
@@ -182,7 +200,7 @@ __global__ void vadd_vec(const float* A, const float* B, float* C, size_t n, siz
 // counted on an mbarrier) and -- after its own tile -- processes the cancelled CTA's tile
 // instead of exiting.  The request's latency hides behind the tile's loads.  One response
 // slot: every thread reads it, the CTA barrier orders those reads before thread 0 re-arms it.
-template <int VW, int UNROLL, int LD, int ST, bool EARLY>
+template <int VW, int UNROLL, int LD, int ST, int EARLY>
 __global__ void vadd_vec_clc(const float* A, const float* B, float* C, size_t n, size_t head,
                              size_t nvec, size_t ntiles)
 {
@@ -204,8 +222,9 @@ __global__ void vadd_vec_clc(const float* A, const float* B, float* C, size_t n,
     float* c = C + head;
     const size_t tile_vecs = static_cast<size_t>(blockDim.x) * UNROLL;
     pdl_launch_dependents();
-    bool waited = !EARLY;
-    if constexpr (!EARLY) pdl_wait();
+    if constexpr (EARLY == 2) prefetch_first_tile<VW>(a, b, blockIdx.x, tile_vecs, nvec);
+    bool waited = EARLY != 1;
+    if constexpr (EARLY != 1) pdl_wait();
 
     uint32_t tile = blockIdx.x, ph = 0;
     while (true) {

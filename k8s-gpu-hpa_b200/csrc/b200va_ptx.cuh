@@ -226,6 +226,14 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t 
                      :: "l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
 
+// Bulk prefetch of [src, src + bytes) into L2 (no destination, nothing to wait for).  src 16-B
+// aligned, bytes a multiple of 16.  L2 is the point of coherence, so prefetching data that an
+// earlier kernel is still writing is harmless.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void bulk_commit()
 {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -76,14 +76,16 @@ def test_early_load_variant_issues_its_loads_before_the_dependency_wait():
     """SASS of the EARLY kernel: both LDG.E.128 come before the first ACQBULK (griddepcontrol.wait)
     and the store after it; the plain kernel waits first."""
     def body(early: int) -> list[str]:
-        fn = f"_ZN6b200va8vadd_vecILi4ELi1ELi0ELi1ELb{early}EEEvPKfS2_Pfmmmm"
+        fn = f"_ZN6b200va8vadd_vecILi4ELi1ELi0ELi1ELi{early}EEEvPKfS2_Pfmmmm"
         out = subprocess.run(["cuobjdump", "-sass", "-fun", fn, capi.LIB_PATH], capture_output=True, text=True).stdout
-        return re.findall(r"\b(LDG\.E\.128|STG\.E\S*\.128|ACQBULK)\b", out)
-    early, plain = body(1), body(0)
-    assert early and plain
+        return re.findall(r"\b(LDG\.E\.128|STG\.E\S*\.128|ACQBULK|UBLKPF\.L2)\b", out)
+    early, plain, prefetch = body(1), body(0), body(2)
+    assert early and plain and prefetch
     assert early.index("ACQBULK") > [i for i, m in enumerate(early) if m.startswith("LDG")][1]
     assert early.index("ACQBULK") < [i for i, m in enumerate(early) if m.startswith("STG")][0]
     assert plain[0] == "ACQBULK"
+    # the always-legal form: two bulk L2 prefetches (A tile, B tile) ahead of the wait, loads and stores after it
+    assert prefetch[:3] == ["UBLKPF.L2", "UBLKPF.L2", "ACQBULK"] and "LDG.E.128" in prefetch[3:]
 
 
 def test_host_rand_recipe_matches_oracle_and_known_answers():
@@ -131,9 +133,10 @@ def test_kernel_names_key_the_ncu_table():
     name what the resolved geometry launches, and an unknown kernel must yield no traffic figure."""
     import bench
 
-    assert pkg.resolve(capi.K_AUTO, 1 << 28).kernel_name() == "vadd_vec<4,1,0,1,0>"
+    assert pkg.resolve(capi.K_AUTO, 1 << 28).kernel_name() == "vadd_vec<4,1,0,1,2>"                         # L2 prefetch ahead of the wait
     assert pkg.resolve(capi.K_AUTO, 1 << 28, capi.F_INPUTS_STABLE).kernel_name() == "vadd_vec<4,1,0,1,1>"
-    assert pkg.resolve(capi.K_AUTO, 1 << 24, capi.F_COLD).kernel_name() == "vadd_vec<4,1,0,0,0>"           # cold-tuned class
+    assert pkg.resolve(capi.K_AUTO, 1 << 24, capi.F_COLD).kernel_name() == "vadd_vec<4,1,0,0,2>"           # cold-tuned class
+    assert pkg.resolve(capi.K_AUTO, 1 << 22, capi.F_COLD | capi.F_INPUTS_STABLE).kernel_name() == "vadd_vec<4,2,0,0,2>"
     assert pkg.resolve(capi.K_AUTO, 1 << 21, capi.F_COLD | capi.F_INPUTS_STABLE).kernel_name() == "vadd_vec<4,4,0,0,1>"
     with pytest.raises(pkg.B200VAError):
         pkg.resolve(capi.K_AUTO, 1 << 20, 0x40)

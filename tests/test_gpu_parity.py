@@ -148,6 +148,11 @@ def test_argument_errors():
         va.add(a, a, tune=t)
     with pytest.raises(pkg.B200VAError):
         va.add(a, a, tune=capi.Tune(kind=capi.K1_VEC128, threads=128, unroll=2, early_loads=7))
+    b = torch.ones_like(a)
+    va.add(a, b, a, tune=capi.Tune(kind=capi.K1_VEC128, threads=128, unroll=2, early_loads=2))      # the L2 prefetch is legal in place
+    va.add(a, b, a, tune=capi.Tune(kind=capi.K1_VEC128, threads=128, unroll=2, early_loads=1))      # register loads are swapped for it
+    torch.cuda.synchronize()
+    assert bool((a == 2.0).all())
 
 
 def test_tuned_geometries_are_all_bit_exact():
@@ -181,8 +186,8 @@ def test_tuned_geometries_are_all_bit_exact():
     for threads in (32, 256, 1024):                                  # 4-byte accesses, U loads per array in flight
         for unroll in (4, 8, 16):
             geos.append(capi.Tune(kind=capi.K4_SCALAR_MLP, threads=threads, unroll=unroll))
-    for kind in (capi.K1_VEC128, capi.K3_VEC256):                    # early loads and the CLC scheduler (K1c)
-        for early in (0, 1):
+    for kind in (capi.K1_VEC128, capi.K3_VEC256):                    # early loads / L2 prefetch and the CLC scheduler (K1c)
+        for early in (0, 1, 2):
             for unroll in (1, 2, 4, 8):
                 for threads in (64, 256, 512):
                     geos.append(capi.Tune(kind=kind, threads=threads, unroll=unroll, ld_hint=0, st_hint=1, early_loads=early, scheduler=1))

@@ -53,7 +53,7 @@ def test_random_lengths_offsets_variants(pools, n, oa, ob, oc, variant, same, st
 @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(n=st.integers(1, POOL), threads=st.sampled_from([32, 64, 96, 128, 256, 320, 512, 1024]),
        unroll=st.sampled_from([1, 2, 4, 8]), cps=st.sampled_from([0, 1, 3]), ld=st.integers(0, 5), stt=st.integers(0, 3),
-       wide=st.booleans(), early=st.booleans(), clc=st.booleans())
+       wide=st.booleans(), early=st.integers(0, 2), clc=st.booleans())
 def test_random_vec_geometries(pools, n, threads, unroll, cps, ld, stt, wide, early, clc):
     ha, hb, a, b = pools
     t = capi.Tune(kind=capi.K3_VEC256 if wide else capi.K1_VEC128, threads=threads, unroll=unroll, ctas_per_sm=0 if clc else cps,

@@ -34,7 +34,7 @@ elif which == "clc":
 elif which == "cold":
     # r02: cold (rotating-buffer) mid sizes -- what closes the launch-boundary bubble: early loads,
     # the CLC scheduler (K1c), whole-wave persistent grids, next to the r01 AUTO classes
-    for early in (0, 1):
+    for early in (0, 1, 2):
         for threads, unroll in ((128, 1), (256, 1), (512, 1), (1024, 1), (128, 2), (256, 2), (512, 2), (128, 4), (256, 4)):
             for ld, st in ((0, 0), (0, 1), (3, 0)):
                 print(K1, threads, unroll, 0, ld, st, 0, 0, 0, early, 0)
@@ -49,7 +49,7 @@ elif which == "cold":
         print(K2, threads, 0, 1, 0, 1, stages, 8192, 2)
 elif which == "headline":
     # r02: 2^28 -- the production geometry, its early-load twin, K1c, and the r01 runners-up
-    for early in (0, 1):
+    for early in (0, 1, 2):
         for threads, unroll in ((512, 1), (384, 1), (256, 1), (1024, 1), (256, 2), (512, 2)):
             print(K1, threads, unroll, 0, 0, 1, 0, 0, 0, early, 0)
         for threads, unroll in ((256, 2), (512, 2), (256, 4), (512, 4), (128, 4), (256, 8)):

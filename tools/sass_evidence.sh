@@ -13,14 +13,15 @@ mkdir -p profiles/$R
   echo "# arch list:"; cuobjdump -lelf $LIB | sed 's/^/#   /'; cuobjdump -lptx $LIB | sed 's/^/#   /'
   echo "# kernels in the library: $(cuobjdump -sass $LIB | grep -c 'Function :')   sha256 $(sha256sum $LIB | cut -c1-16)"
   echo "# mnemonic census over the whole library:"
-  cuobjdump -sass $LIB | grep -oE '\b(LDG\.E[.A-Z0-9]*\.(128|256)|STG\.E[.A-Z0-9]*\.(128|256)|UBLKCP\.S\.G|UBLKCP\.G\.S|UGETNEXTWORKID\.SELFCAST|SYNCS\.[A-Z.0-9]+|ACQBULK|PREEXIT|HMMA[.A-Z0-9]*|UTCHMMA[.A-Z0-9]*)' | sort | uniq -c | sed 's/^/#   /'
+  cuobjdump -sass $LIB | grep -oE '\b(LDG\.E[.A-Z0-9]*\.(128|256)|STG\.E[.A-Z0-9]*\.(128|256)|UBLKCP\.S\.G|UBLKCP\.G\.S|UGETNEXTWORKID\.SELFCAST|UBLKPF\.L2|SYNCS\.[A-Z.0-9]+|ACQBULK|PREEXIT|HMMA[.A-Z0-9]*|UTCHMMA[.A-Z0-9]*)' | sort | uniq -c | sed 's/^/#   /'
   for f in \
-    _ZN6b200va8vadd_vecILi4ELi1ELi0ELi1ELb0EEEvPKfS2_Pfmmmm \
-    _ZN6b200va8vadd_vecILi4ELi1ELi0ELi1ELb1EEEvPKfS2_Pfmmmm \
-    _ZN6b200va8vadd_vecILi4ELi2ELi3ELi0ELb1EEEvPKfS2_Pfmmmm \
-    _ZN6b200va12vadd_vec_clcILi4ELi2ELi0ELi1ELb0EEEvPKfS2_Pfmmmm \
+    _ZN6b200va8vadd_vecILi4ELi1ELi0ELi1ELi0EEEvPKfS2_Pfmmmm \
+    _ZN6b200va8vadd_vecILi4ELi1ELi0ELi1ELi1EEEvPKfS2_Pfmmmm \
+    _ZN6b200va8vadd_vecILi4ELi1ELi0ELi1ELi2EEEvPKfS2_Pfmmmm \
+    _ZN6b200va8vadd_vecILi4ELi2ELi3ELi0ELi1EEEvPKfS2_Pfmmmm \
+    _ZN6b200va12vadd_vec_clcILi4ELi2ELi0ELi1ELi0EEEvPKfS2_Pfmmmm \
     _ZN6b200va12vadd_tma_clcILb0ELi1EEEvPKfS2_Pfmmmjj \
-    _ZN6b200va8vadd_vecILi8ELi1ELi0ELi1ELb0EEEvPKfS2_Pfmmmm ; do
+    _ZN6b200va8vadd_vecILi8ELi1ELi0ELi1ELi0EEEvPKfS2_Pfmmmm ; do
     echo; echo "==================== $(echo $f | c++filt)"
     cuobjdump -sass -fun $f $LIB | grep -E '^\s+/\*[0-9a-f]{4}\*/' | sed -E 's@\s+/\* 0x[0-9a-f]+ \*/\s*$@@'
   done
