@@ -273,22 +273,27 @@ def pcie_probe(a, b, c, ha, hb, hc, sharding, reps: int = 3) -> float:
     return best
 
 
-def cli_strong(gpus: int, cli: str) -> dict:
+def cli_strong(gpus: int, cli: str, devices: list[int] | None = None) -> dict:
     """configs[2] once more through the OTHER host path: the C++ executable's one-thread-per-GPU
     sharding (`vectorAdd --gpus G --n 2^30`, host/vectorAdd.cpp), run by rank 0 after the
     torchrun-side measurements so that this path, too, is exercised wherever the bench runs."""
     import subprocess
     import tempfile
 
+    env = dict(os.environ)
+    if devices:     # the executable numbers its GPUs 0..G-1: show it exactly the GPUs the ranks drove, in rank order
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        base = [v.strip() for v in visible.split(",")] if visible else None
+        env["CUDA_VISIBLE_DEVICES"] = ",".join(base[d] if base else str(d) for d in devices)
     with tempfile.TemporaryDirectory() as d:
         out = os.path.join(d, "cli.json")
         try:
             p = subprocess.run([cli, "--mode", "resident", "--gpus", str(gpus), "--n", "2^30", "--iters", "20", "--json", out],
-                               capture_output=True, text=True, timeout=300)
+                               capture_output=True, text=True, timeout=300, env=env)
             r = json.load(open(out))
         except Exception as e:          # reported, never fatal for the contract line
             return {"error": repr(e)[:200]}
-    return {"command": f"vectorAdd --mode resident --gpus {gpus} --n 2^30 --iters 20", "exit_code": p.returncode,
+    return {"command": f"vectorAdd --mode resident --gpus {gpus} --n 2^30 --iters 20", "devices": devices, "exit_code": p.returncode,
             "value": r["elements_per_s"], "unit": UNIT, "ms_per_step": r["ms_per_pass"], "mismatches": r["mismatches"],
             "frac_of_8TBps_nameplate_per_gpu": r["roofline_frac_of_8TBps_per_gpu"],
             "digest_ok": (int(r["digest_sum"], 16), int(r["digest_xor"], 16)) == DIGEST_2P30}
@@ -537,7 +542,9 @@ def run_ours(args, emit=print) -> None:
         line["strong_2p30"] = strong
         line["loop_2p24"] = loop
     if strong is not None:
-        line["cli_strong_2p30"] = cli_strong(ws, capi.CLI_PATH)
+        numa_of = lambda i: int(capi.lib.b200va_device_numa_node_of(i))      # noqa: E731
+        devs = list(range(ws)) if args.identity_mapping else [device_for_rank(r, ws, ndev, numa_of)[0] for r in range(ws)]
+        line["cli_strong_2p30"] = cli_strong(ws, capi.CLI_PATH, devs)
     if ws == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline_line(n, 1, 5)
         cb.pop("secs")
