@@ -602,7 +602,8 @@ int launch_stream_typed(const void* dA, const void* dB, void* dC, size_t n, doub
     if (grid > 0x7fffffffull) grid = 0x7fffffffull;
     if (grid == 0) grid = 1;
     const size_t ntiles = (nvec + tile_vecs - 1) / tile_vecs;
-    using fn_t = void (*)(const void*, const void*, void*, size_t, size_t, size_t, size_t, S);
+    using fn_t = void (*)(const void*, const void*, void*, size_t, size_t, size_t, size_t, S, int);
+    const int prefetch_first = m >= (size_t{1} << 25) ? 1 : 0;      // >= 128 MiB per array: never L2-resident
     fn_t fn = nullptr;
 #ifdef B200VA_TUNE_MATRIX
     if (unroll == 4) fn = skip_l1_stores ? stream_vec<DT, OP, 4, LD_PLAIN, ST_NA> : stream_vec<DT, OP, 4, LD_PLAIN, ST_PLAIN>;
@@ -611,7 +612,7 @@ int launch_stream_typed(const void* dA, const void* dB, void* dC, size_t n, doub
         if (skip_l1_stores) fn = unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_NA> : stream_vec<DT, OP, 1, LD_PLAIN, ST_NA>;
         else fn = unroll == 2 ? stream_vec<DT, OP, 2, LD_PLAIN, ST_PLAIN> : stream_vec<DT, OP, 1, LD_PLAIN, ST_PLAIN>;
     }
-    return launch_kernel(fn, static_cast<unsigned>(grid), threads, 0, st, dA, dB, dC, n, head, nvec, ntiles, s);
+    return launch_kernel(fn, static_cast<unsigned>(grid), threads, 0, st, dA, dB, dC, n, head, nvec, ntiles, s, prefetch_first);
 }
 
 template <int DT>

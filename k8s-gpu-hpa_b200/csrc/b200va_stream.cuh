@@ -136,9 +136,12 @@ __device__ __forceinline__ void op_elem(const void* A, const void* B, void* C, s
 
 // ---- the streaming kernel ----------------------------------------------------------
 // `head` elements peeled in front, `nvec` 16-byte vectors, scalar tail; CTA 0 does the edges.
+// prefetch_first != 0: thread 0 bulk-prefetches the CTA's first input tile(s) into L2 ahead of the
+// programmatic dependency on the previous launch (always legal: L2 is the coherence point; see
+// vadd_vec EARLY = 2) -- set by the dispatcher for arrays that cannot be L2-resident.
 template <int DT, int OP, int UNROLL, int LD, int ST>
 __global__ void stream_vec(const void* A, const void* B, void* C, size_t n, size_t head, size_t nvec, size_t ntiles,
-                           typename dt_traits<DT>::scalar s)
+                           typename dt_traits<DT>::scalar s, int prefetch_first)
 {
     constexpr int ES = dt_traits<DT>::size;
     constexpr int EPV = 16 / ES;
@@ -148,6 +151,12 @@ __global__ void stream_vec(const void* A, const void* B, void* C, size_t n, size
     unsigned char* c = static_cast<unsigned char*>(C) + head * ES;
     const size_t tile_vecs = static_cast<size_t>(blockDim.x) * UNROLL;
     pdl_launch_dependents();
+    if (prefetch_first && threadIdx.x == 0 && blockIdx.x * tile_vecs < nvec) {
+        const size_t t0 = blockIdx.x * tile_vecs;
+        const uint32_t bytes = static_cast<uint32_t>((nvec - t0 < tile_vecs ? nvec - t0 : tile_vecs) * 16);
+        bulk_prefetch_l2(a + t0 * 16, bytes);
+        if constexpr (binary) bulk_prefetch_l2(b + t0 * 16, bytes);
+    }
     pdl_wait();
 
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {

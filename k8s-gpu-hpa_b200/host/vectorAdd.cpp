@@ -322,9 +322,18 @@ struct Nvml {
     ~Nvml() { if (lib && shut) shut(); }
 };
 
+// B200VA_TRACE_STARTUP=1: milliseconds since process start at each step of the sample flow, on stderr
+// (where does one ./vectorAdd process of the reference's 5000-process loop spend its time?).
+struct StartupTrace {
+    const bool on = [] { const char* e = std::getenv("B200VA_TRACE_STARTUP"); return e && e[0] == '1'; }();
+    const clk::time_point t0 = clk::now();
+    void mark(const char* what) const { if (on) std::fprintf(stderr, "[startup] %-28s %9.3f ms\n", what, secs_since(t0) * 1e3); }
+};
+
 // ------------------------------------------------------------------ sample mode (a2..a7)
 int run_sample(const Options& o)
 {
+    const StartupTrace trace;
     const size_t n = o.n;
     const size_t size = n * sizeof(float);
     std::printf("[Vector addition of %zu elements]\n", n);
@@ -345,8 +354,10 @@ int run_sample(const Options& o)
         });
     }
 
+    trace.mark("host vectors filled");
     float *d_A = nullptr, *d_B = nullptr, *d_C = nullptr;
     ck(cudaMalloc(&d_A, size ? size : 4), "allocate device vector A");
+    trace.mark("first cudaMalloc (context)");
     ck(cudaMalloc(&d_B, size ? size : 4), "allocate device vector B");
     ck(cudaMalloc(&d_C, size ? size : 4), "allocate device vector C");
 
@@ -358,12 +369,14 @@ int run_sample(const Options& o)
     unsigned grid = 0, block = 0;
     va(b200va_resolve(o.variant, n, &tune), "resolve kernel geometry");
     va(b200va_geometry(&tune, n, 0, &grid, &block, nullptr), "resolve kernel geometry");
+    trace.mark("H2D copies done");
     std::printf("CUDA kernel launch with %u blocks of %u threads\n", grid, block);
     cudaStream_t st;
     ck(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "create stream");
     va(b200va_add_f32_loop(d_A, d_B, d_C, n, o.variant, o.iters, o.graph, st), "launch vectorAdd kernel");
     ck(cudaStreamSynchronize(st), "launch vectorAdd kernel");
 
+    trace.mark("kernel(s) done");
     std::printf("Copy output data from the CUDA device to the host memory\n");
     ck(cudaMemcpy(h_C, d_C, size, cudaMemcpyDeviceToHost), "copy vector C from device to host");
 
@@ -378,12 +391,15 @@ int run_sample(const Options& o)
         std::printf("Test SKIPPED (--verify none)\n");   // never claim a pass that was not checked
     }
 
+    trace.mark("D2H + verify done");
     ck(cudaStreamDestroy(st), "destroy stream");
     ck(cudaFree(d_A), "free device vector A");
     ck(cudaFree(d_B), "free device vector B");
     ck(cudaFree(d_C), "free device vector C");
     std::free(h_A); std::free(h_B); std::free(h_C);
+    trace.mark("device memory freed");
     ck(cudaDeviceReset(), "deinitialize the device");
+    trace.mark("cudaDeviceReset done");
     std::printf("Done\n");
     return EXIT_SUCCESS;
 }

@@ -76,6 +76,9 @@ if has sanitizer; then
   # the round-2 kernels under compute-sanitizer: early-load form, K1c (mbarrier + try_cancel response slot), K2c after the edge fix
   cat > "$OUT/san_geos.txt" <<'GEO'
 2 512 1 0 0 1 0 0 0 1 0
+2 512 1 0 0 1 0 0 0 2 0
+2 512 2 0 0 0 0 0 0 2 0
+4 256 2 0 0 1 0 0 0 2 1
 2 256 4 0 0 0 0 0 0 1 0
 2 256 2 0 0 1 0 0 0 0 1
 2 128 4 0 0 1 0 0 0 1 1
@@ -114,6 +117,19 @@ if has ncu24; then
   timeout 600 ncu --set full --clock-control none --cache-control none --import-source on -k regex:vadd_ -s 60 -c 3 -f -o "$OUT/prof_loop_2p24_hot" \
       $PKG/vectorAdd --mode resident --n 2^24 --iters 200 --verify none >> "$OUT/ncu_full.log" 2>&1
   note "ncu 2^24 loop (no cache flush between replays) exit=$?"
+fi
+
+if has ncucold; then
+  # DRAM bytes and L2 hit rate of the three ahead-of-the-wait forms on cold 2^23 buffers (ncu serialises launches, so
+  # the overlap itself is not visible here -- the point is that the prefetch adds no DRAM traffic)
+  printf "2 512 2 0 0 0 0 0 0 0 0\n2 512 2 0 0 0 0 0 0 2 0\n2 512 2 0 0 0 0 0 0 1 0\n" > "$OUT/cold_trio.txt"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:vadd_vec -c 12 -f -o "$OUT/prof_cold_trio_2p23" \
+      $PKG/b200va_tune --n $((1<<23)) --reps 2 --warmup 0 --rounds 1 --cold < "$OUT/cold_trio.txt" > "$OUT/ncu_cold.log" 2>&1
+  note "ncu cold trio 2^23 exit=$?"
+fi
+
+if has stream; then
+  timeout 900 python tools/stream_bench.py > "$OUT/stream_bench.jsonl" 2> "$OUT/stream_bench.err"; note "stream bench exit=$?"
 fi
 
 if has ncuskew; then
