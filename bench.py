@@ -24,6 +24,8 @@ cpu_baseline / --impl reference
              faster reported.  The oracle is never on the product path.
 The other BASELINE.json configs that fit a bench run ride in the same line:
 strong_2p30  configs[2]: global N = 2^30 sharded over the N ranks (2^30/N per GPU), fixed total
+cli_strong_2p30  the same shape through the C++ executable's one-thread-per-GPU path (`vectorAdd --gpus N`),
+             run by rank 0 on exactly the GPUs the ranks drove
 loop_2p24    configs[4]: 5000 launches of N = 2^24 in 50-launch CUDA graphs on each GPU
 """
 from __future__ import annotations

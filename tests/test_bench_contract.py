@@ -66,3 +66,38 @@ def test_digest_constants_are_the_oracles():
 
     assert oracle.ctr_vadd_digest(1 << 24) == bench.DIGEST_2P24
     assert oracle.ctr_vadd_digest(1 << 30) == bench.DIGEST_2P30
+
+
+def test_cli_strong_leg_shows_the_executable_exactly_the_ranks_gpus(tmp_path, monkeypatch):
+    """bench.cli_strong: rank 0 runs `vectorAdd --gpus G --n 2^30` on the GPUs the ranks drove (rank order),
+    composed with any CUDA_VISIBLE_DEVICES already in force; its JSON is parsed into the bench line."""
+    import stat
+
+    import bench
+
+    fake = tmp_path / "vectorAdd"
+    fake.write_text("""#!/usr/bin/env python3
+import json, os, sys
+out = sys.argv[sys.argv.index("--json") + 1]
+json.dump({"elements_per_s": 4.7e12, "ms_per_pass": 0.2268, "mismatches": 0, "roofline_frac_of_8TBps_per_gpu": 0.9,
+           "digest_sum": "0fd8e36879aed49f", "digest_xor": "0f23c595", "seen": os.environ.get("CUDA_VISIBLE_DEVICES"),
+           "argv": sys.argv[1:]}, open(out, "w"))
+""")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    seen = {}
+    real_load = json.load
+
+    def spy(f):
+        d = real_load(f)
+        seen.update(d)
+        return d
+
+    monkeypatch.setattr(bench.json, "load", spy)
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES", raising=False)
+    r = bench.cli_strong(4, str(fake), [0, 4, 1, 5])
+    assert r["digest_ok"] and r["exit_code"] == 0 and r["value"] == 4.7e12 and r["devices"] == [0, 4, 1, 5]
+    assert seen["seen"] == "0,4,1,5" and seen["argv"][:6] == ["--mode", "resident", "--gpus", "4", "--n", "2^30"]
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "2,3,6,7,GPU-x,9")          # indices are relative to what is already visible
+    bench.cli_strong(2, str(fake), [0, 4])
+    assert seen["seen"] == "2,GPU-x"
+    assert "error" in bench.cli_strong(1, str(tmp_path / "missing"), [0])     # reported, never fatal
