@@ -103,6 +103,35 @@ def test_stager_register_once_on_plain_malloced_arrays():
             st.add(pa, pb, pc, mode=9)
 
 
+def test_device_entry_point_on_host_mapped_memory_large_enough_for_the_prefetch_form():
+    """b200va_add_f32 on pinned host memory addressed directly by the GPU (UVA), at a size where AUTO
+    resolves to the L2-prefetch form: the bulk prefetch is only a hint, the result must be the oracle's."""
+    n = (1 << 25) + 77
+    t = capi.resolve(capi.K_AUTO, n)
+    assert t.early_loads == 2
+    bufs = [va.PinnedBuffer(n) for _ in range(3)]
+    try:
+        ha, hb, hc = (b.array for b in bufs)
+        ha[:] = oracle.fill_ctr(n, 0x0A, 5)
+        hb[:] = oracle.fill_ctr(n, 0x0B, 5)
+        hc[:] = -1.0
+        stream = torch.cuda.current_stream().cuda_stream
+        for _ in range(2):                                   # twice: the second launch prefetches while the first drains
+            rc = capi.lib.b200va_add_f32(ha.ctypes.data, hb.ctypes.data, hc.ctypes.data, n, capi.K_AUTO, stream)
+            assert rc == capi.OK, capi.strerror(rc)
+        torch.cuda.synchronize()
+        assert oracle.first_mismatch(np.array(hc), oracle.vadd(np.array(ha), np.array(hb))) == -1
+        # the host rewrites an input between two launches: the second launch must see the new values
+        ha[: 1 << 20] = 0.5
+        rc = capi.lib.b200va_add_f32(ha.ctypes.data, hb.ctypes.data, hc.ctypes.data, n, capi.K_AUTO, stream)
+        assert rc == capi.OK
+        torch.cuda.synchronize()
+        assert oracle.first_mismatch(np.array(hc), oracle.vadd(np.array(ha), np.array(hb))) == -1
+    finally:
+        for b in bufs:
+            b.free()
+
+
 def test_concurrent_callers_on_one_device():
     """The library is re-entrant: four host threads, each with its own stream and its own stager, call the
     device entry points and the host-buffer path at the same time on the same GPU (ctypes releases the GIL)."""
