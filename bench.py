@@ -52,6 +52,7 @@ BYTES_PER_ELEM = 12  # 4 read A + 4 read B + 4 write C
 # oracle.ctr_vadd_digest(1 << 30) / (1 << 24): asserted against the oracle in tests/test_oracle.py
 DIGEST_2P30 = (0x0FD8E36879AED49F, 0x0F23C595)
 DIGEST_2P24 = (0x003F639456AC9687, 0x064A9499)
+READ_ONLY_CEILING_GBPS = 7436.0   # pure read stream (A and B in, nothing out) with the production geometry: profiles/r02/a_channel_skew.jsonl
 LINK_ALONE_MS_PER_2P28 = 40.8   # one GPU's PCIe Gen5 x16 link, 2 GiB in + 1 GiB out concurrently (profiles/r01/l_pcie_probe.jsonl)
 
 
@@ -533,6 +534,9 @@ def run_ours(args, emit=print) -> None:
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_ELEM * n,
+                     "frac_of_read_only_ceiling": achieved / READ_ONLY_CEILING_GBPS,
+                     "read_only_ceiling": f"{READ_ONLY_CEILING_GBPS:.0f} GB/s: what a pure read stream reaches on this part (committed probe, "
+                                          "profiles/r02/a_channel_skew.jsonl; 91 % of the 8.18 TB/s pin rate) -- a harder denominator than the torch copy peak",
                      "kernel": f"b200va::{kname} grid {grid.value} x {block.value} threads (one launch per step)"},
         "clocks": sampler.summary(),
         "gpu_launches": launches,
