@@ -267,6 +267,18 @@ int b200va_device_numa_node_of(int device);
 int b200va_stream(int op, int dtype, const void *dA, const void *dB, void *dC, size_t n,
                   double scalar, void *stream);
 
+/* ---- ceiling probes (measurement aids; not part of the reference's surface) -------------
+ * The production launch geometry with one side of the add's traffic removed, so a harness can
+ * measure on the spot what the HBM gives each kind of stream (bench.py reports the add as a
+ * fraction of the READ2 rate).  n is rounded down to a multiple of 4; pointers 16-byte aligned.
+ *   READ2  load A and B, store one float per CTA into C (8 B/element read)
+ *   FILL   C = 1.0f, nothing is read                       (4 B/element written)
+ *   COPY   C = A                                            (4 B read + 4 B written per element) */
+#define B200VA_PROBE_READ2  0
+#define B200VA_PROBE_FILL   1
+#define B200VA_PROBE_COPY   2
+int b200va_probe_f32(int kind, const float *dA, const float *dB, float *dC, size_t n, void *stream);
+
 /* ---- shard arithmetic (8(e)): contiguous equal shards, starts on 16-byte multiples --- */
 int b200va_shard_range(size_t n, int world, int rank, size_t *begin, size_t *end);
 

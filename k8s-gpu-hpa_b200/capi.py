@@ -25,6 +25,7 @@ ERR_CUDA_BASE = -1000
 K_AUTO, K0_SCALAR, K1_VEC128, K2_TMA, K3_VEC256, K4_SCALAR_MLP = 0, 1, 2, 3, 4, 5
 F_INPUTS_STABLE, F_COLD = 1, 2
 STAGE_AUTO, STAGE_SLOTS, STAGE_ZEROCOPY, STAGE_LANES, STAGE_BOUNCE, STAGE_REGISTER = -1, 0, 1, 2, 3, 4
+PROBES = {"read2": 0, "fill": 1, "copy": 2}
 OPS = {"copy": 0, "scale": 1, "add": 2, "triad": 3}
 DTYPES = {"f32": 0, "f64": 1, "f16": 2, "bf16": 3}
 VARIANTS = {"auto": K_AUTO, "k0": K0_SCALAR, "k1": K1_VEC128, "k2": K2_TMA, "k3": K3_VEC256}
@@ -107,6 +108,7 @@ _SIGS = {
     "b200va_device_numa_node": (_I, []),
     "b200va_device_numa_node_of": (_I, [_I]),
     "b200va_stream": (_I, [_I, _I, _P, _P, _P, _SZ, C.c_double, _P]),
+    "b200va_probe_f32": (_I, [_I, _P, _P, _P, _SZ, _P]),
     "b200va_shard_range": (_I, [_SZ, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
 }
 def _bind(handle) -> None:

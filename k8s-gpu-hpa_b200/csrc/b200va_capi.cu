@@ -959,6 +959,29 @@ int b200va_stream(int op, int dtype, const void* dA, const void* dB, void* dC, s
     return B200VA_ERR_VARIANT;
 }
 
+// ------------------------------------------------------------------ ceiling probes
+int b200va_probe_f32(int kind, const float* dA, const float* dB, float* dC, size_t n, void* stream)
+{
+    if (kind < B200VA_PROBE_READ2 || kind > B200VA_PROBE_COPY) return B200VA_ERR_VARIANT;
+    const b200va_devinfo_t* di = nullptr;
+    RC_TRY(current_dev_info(&di));
+    const size_t nvec = n / 4;
+    if (nvec == 0) return B200VA_OK;
+    if (!dC || (kind != B200VA_PROBE_FILL && !dA) || (kind == B200VA_PROBE_READ2 && !dB)) return B200VA_ERR_INVALID;
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(dC) | (kind != B200VA_PROBE_FILL ? reinterpret_cast<uintptr_t>(dA) : 0) |
+                           (kind == B200VA_PROBE_READ2 ? reinterpret_cast<uintptr_t>(dB) : 0);
+    if (bits & 15u) return B200VA_ERR_ALIGN;
+    const size_t blocks = (nvec + 511) / 512;
+    if (blocks > 0x7fffffffull) return B200VA_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = static_cast<unsigned>(blocks);
+    switch (kind) {
+        case B200VA_PROBE_READ2: return launch_kernel(probe_read2, grid, 512u, 0, st, dA, dB, dC, nvec);
+        case B200VA_PROBE_FILL:  return launch_kernel(probe_fill, grid, 512u, 0, st, dC, nvec, 1.0f);
+        default:                 return launch_kernel(probe_copy, grid, 512u, 0, st, dA, dC, nvec);
+    }
+}
+
 // ------------------------------------------------------------------ shard arithmetic
 int b200va_shard_range(size_t n, int world, int rank, size_t* begin, size_t* end)
 {

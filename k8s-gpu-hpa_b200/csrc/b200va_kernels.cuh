@@ -521,6 +521,39 @@ vadd_tma_clc(const float* A, const float* B, float* C, size_t n, size_t head, si
     }
 }
 
+// ---------------------------------------------------------------- ceiling probes
+// The production geometry (512 threads x one 128-bit vector per array) with one side of the
+// traffic removed: what the HBM gives a pure read stream, a pure write stream and a 1:1 copy,
+// next to the add's 2:1 mix (b200va_probe_f32; profiles/r02/README.md section 1a).
+__global__ void probe_read2(const float* A, const float* B, float* C, size_t nvec)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    float sum = 0.f;
+    if (v < nvec) {
+        const f32x4 a = ldg128<LD_PLAIN>(A + v * 4, 0), b = ldg128<LD_PLAIN>(B + v * 4, 0);   // asm volatile: never elided
+        sum = a.x + b.x + a.y + b.y + a.z + b.z + a.w + b.w;
+    }
+    if (threadIdx.x == 0) C[blockIdx.x] = sum;          // 4 bytes per CTA: 0.02 % of the traffic
+}
+
+__global__ void probe_fill(float* C, size_t nvec, float value)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (v < nvec) stg128<ST_NA>(C + v * 4, f32x4{value, value, value, value}, 0);
+}
+
+__global__ void probe_copy(const float* A, float* C, size_t nvec)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (v < nvec) stg128<ST_NA>(C + v * 4, ldg128<LD_PLAIN>(A + v * 4, 0), 0);
+}
+
 // ---------------------------------------------------------------- support kernels
 __device__ __forceinline__ uint64_t splitmix64(uint64_t z)
 {

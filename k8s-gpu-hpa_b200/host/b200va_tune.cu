@@ -12,8 +12,8 @@
 //                                 every launch streams from HBM (what the stager's chunks see)
 //                 [--skew BYTES]  carve A, B, C out of ONE allocation with B at +BYTES and C at
 //                                 +2*BYTES relative to their natural n*4 spacing (HBM channel phase)
-//                 [--probes]      also time the ceiling probes on the same buffers: read2 (two
-//                                 arrays in, nothing out), fill (one array out), copy (1 in 1 out)
+//                 [--probes]      also time the ceiling probes (b200va_probe_f32) on the same buffers: read2
+//                                 (two arrays in, nothing out), fill (one array out), copy (1 in 1 out)
 //                 < geometries.txt
 //
 // Not part of the reference's surface: a development tool for profiles/*.
@@ -28,7 +28,6 @@
 #include <vector>
 
 #include "../../include/b200va.h"
-#include "../csrc/b200va_ptx.cuh"
 
 #define CK(expr)                                                                           \
     do {                                                                                   \
@@ -47,32 +46,6 @@
             std::exit(1);                                                                  \
         }                                                                                  \
     } while (0)
-
-// ---- ceiling probes: the production geometry (512 threads x one 128-bit vector) with one side
-// of the traffic removed.  They bracket what the HBM gives a pure read stream, a pure write
-// stream and a 1:1 mix, next to the add's 2:1.
-using b200va::f32x4;
-
-__global__ void probe_read2(const float* A, const float* B, float* C, size_t nvec)
-{
-    const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (v >= nvec) return;
-    const f32x4 a = b200va::ldg128<b200va::LD_PLAIN>(A + v * 4, 0), b = b200va::ldg128<b200va::LD_PLAIN>(B + v * 4, 0);
-    // inputs are in [0,1): the sum is never negative, so the store never executes, but the loads must
-    if (a.x + b.x + a.y + b.y + a.z + b.z + a.w + b.w < 0.f) C[v] = a.x;
-}
-
-__global__ void probe_fill(float* C, size_t nvec, float value)
-{
-    const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (v < nvec) b200va::stg128<b200va::ST_NA>(C + v * 4, f32x4{value, value, value, value}, 0);
-}
-
-__global__ void probe_copy(const float* A, float* C, size_t nvec)
-{
-    const size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (v < nvec) b200va::stg128<b200va::ST_NA>(C + v * 4, b200va::ldg128<b200va::LD_PLAIN>(A + v * 4, 0), 0);
-}
 
 int main(int argc, char** argv)
 {
@@ -177,7 +150,6 @@ int main(int argc, char** argv)
         CK(cudaEventElapsedTime(&total, e0, e1));
         return static_cast<double>(total) / reps;
     };
-    const unsigned pgrid = static_cast<unsigned>((n / 4 + 511) / 512);
     std::vector<double> p_read, p_fill, p_copy;
     for (int r = 0; r < rounds; ++r) {
         for (auto& g : geos) {
@@ -185,10 +157,9 @@ int main(int argc, char** argv)
             g.ms.push_back(time_batch([&](int s) { VA(b200va_add_f32_tuned(A(s), B(s), C(s), n, &g.t, st)); }));
         }
         if (probes) {
-            p_read.push_back(time_batch([&](int s) { probe_read2<<<pgrid, 512, 0, st>>>(A(s), B(s), C(s), n / 4); }));
-            p_fill.push_back(time_batch([&](int s) { probe_fill<<<pgrid, 512, 0, st>>>(C(s), n / 4, 1.f); }));
-            p_copy.push_back(time_batch([&](int s) { probe_copy<<<pgrid, 512, 0, st>>>(A(s), C(s), n / 4); }));
-            CK(cudaGetLastError());
+            p_read.push_back(time_batch([&](int s) { VA(b200va_probe_f32(B200VA_PROBE_READ2, A(s), B(s), C(s), n, st)); }));
+            p_fill.push_back(time_batch([&](int s) { VA(b200va_probe_f32(B200VA_PROBE_FILL, nullptr, nullptr, C(s), n, st)); }));
+            p_copy.push_back(time_batch([&](int s) { VA(b200va_probe_f32(B200VA_PROBE_COPY, A(s), nullptr, C(s), n, st)); }));
         }
     }
     const double bytes = 12.0 * static_cast<double>(n);

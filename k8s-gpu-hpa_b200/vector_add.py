@@ -135,6 +135,14 @@ def stream(op: str, a, b=None, out=None, *, scalar: float = 0.0, stream=None):
     return out
 
 
+def probe(kind: str, a, b, c, *, stream=None):
+    """Ceiling probe (b200va_probe_f32): 'read2' loads a and b, 'fill' stores c, 'copy' c = a.  c is clobbered."""
+    torch = _torch()
+    with torch.cuda.device(c.device):
+        check(lib.b200va_probe_f32(capi.PROBES[kind], a.data_ptr() if a is not None else None, b.data_ptr() if b is not None else None,
+                                   _dev_ptr(c, "c"), c.numel(), _stream_ptr(stream)), "b200va_probe_f32")
+
+
 def fill_ctr(out, seed: int, first: int = 0, *, stream=None):
     """Counter generator on the device: out[i] = ctr(seed, first + i)."""
     torch = _torch()

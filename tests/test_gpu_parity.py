@@ -348,6 +348,34 @@ def test_clc_scheduled_tma_kernel_ragged_sizes_and_offsets():
     assert va.digest(z) == oracle.ctr_vadd_digest(n) and va.verify(x, y, z) == (0, -1)
 
 
+def test_ceiling_probes_move_the_bytes_they_claim():
+    """b200va_probe_f32: FILL writes 1.0 to every vector element, COPY copies A, READ2 leaves one partial sum per CTA
+    (so its loads cannot have been elided) and touches nothing else; argument errors are refused."""
+    n = (1 << 20) + 4 * 123
+    ha, hb = oracle.fill_ctr(n, 0x0A), oracle.fill_ctr(n, 0x0B)
+    a, b = dev(ha), dev(hb)
+    c = torch.full((n,), -3.0, dtype=torch.float32, device="cuda")
+    va.probe("fill", None, None, c)
+    assert bool((c == 1.0).all())
+    va.probe("copy", a, None, c)
+    assert_bits_equal(c, ha, "copy probe")
+    c.fill_(-3.0)
+    va.probe("read2", a, b, c)
+    torch.cuda.synchronize()
+    ctas = (n // 4 + 511) // 512
+    got = c.cpu().numpy()
+    assert (got[ctas:] == -3.0).all()
+    for k in (0, 1, ctas - 1):                     # thread 0 of CTA k summed vector 512 k of A and of B
+        v = 512 * k * 4
+        want = np.float32(0)
+        for x, y in zip(ha[v:v + 4], hb[v:v + 4]):
+            want = np.float32(np.float32(want + x) + y)
+        assert got[k] == want
+    assert capi.lib.b200va_probe_f32(7, a.data_ptr(), b.data_ptr(), c.data_ptr(), n, None) == capi.ERR_VARIANT
+    assert capi.lib.b200va_probe_f32(0, a.data_ptr() + 4, b.data_ptr(), c.data_ptr(), n, None) == capi.ERR_ALIGN
+    assert capi.lib.b200va_probe_f32(0, None, b.data_ptr(), c.data_ptr(), n, None) == capi.ERR_INVALID
+
+
 def test_device_verify_and_digest_detect_a_single_flipped_bit():
     n = 1_000_001
     a = torch.empty(n, dtype=torch.float32, device="cuda")
