@@ -884,8 +884,11 @@ int b200va_fill_ctr_f32(float* d, size_t n, uint64_t seed, uint64_t first, void*
     const b200va_devinfo_t* di = nullptr;
     RC_TRY(current_dev_info(&di));
     if (n == 0) return B200VA_OK;
-    fill_ctr<<<support_grid(di, n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        d, n, seed * 0x9E3779B97F4A7C15ull + first);
+    const uint64_t base = seed * 0x9E3779B97F4A7C15ull + first;
+    if ((reinterpret_cast<uintptr_t>(d) & 15u) == 0)      // the usual case: one STG.128 per four elements
+        fill_ctr_vec<<<support_grid(di, (n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, n, base);
+    else
+        fill_ctr<<<support_grid(di, n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d, n, base);
     return cuda_err(cudaGetLastError());
 }
 
@@ -916,7 +919,9 @@ int b200va_verify_f32(const float* dA, const float* dB, const float* dC, size_t 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto* res = reinterpret_cast<unsigned long long*>(d_result);
     reset_verify<<<1, 1, 0, st>>>(res);
-    if (n) verify_bits<<<support_grid(di, n, 256), 256, 0, st>>>(dA, dB, dC, n, res);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | reinterpret_cast<uintptr_t>(dC)) & 15u) == 0;
+    if (n && aligned) verify_bits_vec<<<support_grid(di, (n + 3) / 4, 256), 256, 0, st>>>(dA, dB, dC, n, res);
+    else if (n) verify_bits<<<support_grid(di, n, 256), 256, 0, st>>>(dA, dB, dC, n, res);
     return cuda_err(cudaGetLastError());
 }
 
@@ -928,7 +933,8 @@ int b200va_digest_f32(const float* d, size_t n, uint64_t* d_out, void* stream)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto* out = reinterpret_cast<unsigned long long*>(d_out);
     reset_digest<<<1, 1, 0, st>>>(out);
-    if (n) digest_bits<<<support_grid(di, n, 256), 256, 0, st>>>(d, n, out);
+    if (n && (reinterpret_cast<uintptr_t>(d) & 15u) == 0) digest_bits_vec<<<support_grid(di, (n + 3) / 4, 256), 256, 0, st>>>(d, n, out);
+    else if (n) digest_bits<<<support_grid(di, n, 256), 256, 0, st>>>(d, n, out);
     return cuda_err(cudaGetLastError());
 }
 

@@ -348,6 +348,28 @@ def test_clc_scheduled_tma_kernel_ragged_sizes_and_offsets():
     assert va.digest(z) == oracle.ctr_vadd_digest(n) and va.verify(x, y, z) == (0, -1)
 
 
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 1023, 1 << 16, (1 << 20) + 3, 7_000_001])
+def test_support_kernels_vector_and_scalar_paths_agree(n):
+    """fill_ctr / verify / digest have a 128-bit form for 16-byte-aligned pointers and a scalar one otherwise:
+    both must give the host generator's values, the oracle's digest and the same verdict (count and FIRST bad index)."""
+    big = torch.empty(3 * (n + 8), dtype=torch.float32, device="cuda")
+    for off in (0, 1):                                    # 16-byte aligned / misaligned views
+        a, b, c = (big[k * (n + 8) + off: k * (n + 8) + off + n] for k in range(3))
+        va.fill_ctr(a, 0x0A, 12345)
+        va.fill_ctr(b, 0x0B, 12345)
+        ha, hb = oracle.fill_ctr(n, 0x0A, 12345), oracle.fill_ctr(n, 0x0B, 12345)
+        assert_bits_equal(a, ha, f"fill off={off}")
+        assert_bits_equal(b, hb, f"fill off={off}")
+        va.add(a, b, c)
+        assert va.verify(a, b, c) == (0, -1)
+        assert va.digest(c) == oracle.bits_digest(oracle.vadd(ha, hb))
+        if n >= 5:
+            bad = sorted({n - 1, n // 2, 4 if n > 8 else 2})        # the ragged tail, the middle, an early element
+            for i in bad:
+                c.view(torch.int32)[i] ^= 0x10
+            assert va.verify(a, b, c) == (len(bad), bad[0]), (off, bad)
+
+
 def test_ceiling_probes_move_the_bytes_they_claim():
     """b200va_probe_f32: FILL writes 1.0 to every vector element, COPY copies A, READ2 leaves one partial sum per CTA
     (so its loads cannot have been elided) and touches nothing else; argument errors are refused."""
