@@ -51,12 +51,13 @@ def test_replay_reference_shape_vs_sustained_loop():
     assert hr.would_scale_up(6.0) and not hr.would_scale_up(5.2)
 
 
-def test_recorded_gpu_run_replays_to_the_same_decisions():
-    """profiles/r01/aa_hpa_trigger_replay.jsonl: NVML utilisation measured on a B200 while the
+@pytest.mark.parametrize("rel", ["r01/aa_hpa_trigger_replay.jsonl", "r02/e_hpa_trigger_replay.jsonl"])
+def test_recorded_gpu_run_replays_to_the_same_decisions(rel):
+    """profiles/r0x/*_hpa_trigger_replay.jsonl: NVML utilisation measured on a B200 while the
     load generator ran at several duty cycles; the offline rule + HPA must agree with it."""
     import json
 
-    path = os.path.join(ROOT, "profiles", "r01", "aa_hpa_trigger_replay.jsonl")
+    path = os.path.join(ROOT, "profiles", *rel.split("/"))
     if not os.path.exists(path):
         pytest.skip("recorded run not present")
     rows = [json.loads(l) for l in open(path)]
