@@ -19,7 +19,17 @@
  *     a6  fabs(h_A[i] + h_B[i] - h_C[i]) > 1e-5  -> "Result verification failed"
  * (Its launch shape -- N = 50000, 256 threads, (N+255)/256 blocks, guard i < N -- is
  * corroborated by NVIDIA's int-typed derivatives shipped with this toolkit:
- * /usr/local/cuda/extras/CUPTI/samples/cupti_nvtx/cupti_nvtx.cu:41-53,71,150-153.)
+ * /usr/local/cuda/extras/CUPTI/samples/cupti_nvtx/cupti_nvtx.cu:41-53,71,150-153; and the
+ * FLOAT recipe itself by another NVIDIA derivative of the same sample on this disk,
+ * /usr/local/cuda/extras/CUPTI/samples/cuda_memory_trace/memory_trace.cu:
+ *   :23-35    __global__ VectorAdd(const float*, const float*, float*, int N):
+ *             i = blockIdx.x * blockDim.x + threadIdx.x; if (i < N) pC[i] = pA[i] + pB[i];
+ *   :101-105  pHostA[n] = rand() / (float)RAND_MAX; pHostB[n] = rand() / (float)RAND_MAX;
+ *             interleaved per index, and no srand() anywhere in the file
+ *   :116-118  dim3 block(256); grid = ceil(nElements / 256).
+ * That is NVIDIA's code, not the reference's image: it corroborates a2 and a4 as restated
+ * here (tests/test_oracle.py re-reads those lines when the file is present); it does not
+ * pin the reference.)
  * Because binary32 RNE addition has exactly one correct result for non-NaN operands,
  * the oracle is pinned by the IEEE-754 standard instead: oracle_softfloat_add_f32()
  * below is an integer-only implementation written from the standard, and

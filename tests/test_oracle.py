@@ -170,3 +170,26 @@ def test_cpu_baseline_reports_both_store_kinds():
     cfg = oracle.best_cpu_config(1 << 20)
     assert set(k.split(" ")[0] for k in cfg["tried"]) == {"regular", "non-temporal"}
     assert cfg["rate"] == max(d["elements_per_s"] for d in cfg["tried"].values()) and cfg["threads"] >= 1
+
+
+def test_on_disk_nvidia_derivative_carries_the_restated_float_recipe():
+    """The toolkit ships an NVIDIA derivative of the vectorAdd sample with FLOAT operands
+    (CUPTI samples, cuda_memory_trace/memory_trace.cu).  It is not the reference's image, but it
+    corroborates what oracle/vadd_oracle.c restates from recollection: the kernel body, the
+    interleaved never-seeded rand()/(float)RAND_MAX fill, 256-thread blocks."""
+    import re
+
+    path = "/usr/local/cuda/extras/CUPTI/samples/cuda_memory_trace/memory_trace.cu"
+    if not os.path.exists(path):
+        pytest.skip("CUPTI samples not installed on this machine")
+    src = open(path).read()
+    flat = re.sub(r"\s+", " ", src)
+    assert re.search(r"VectorAdd\( const float \*pA, const float \*pB, float \*pC, int N\)", flat)
+    assert "int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < N) { pC[i] = pA[i] + pB[i]; }" in flat
+    assert "pHostA[n] = rand() / (float)RAND_MAX; pHostB[n] = rand() / (float)RAND_MAX;" in flat      # A then B, per index
+    assert "srand" not in src                                                                           # glibc default seed 1
+    assert "dim3 block(256);" in src
+    # ... and that recipe, run through the oracle, is the one whose known answers are pinned above
+    a, b = oracle.fill_rand(4)
+    assert [int(v) for v in a.view(np.uint32)] == [k[0] for k in (SURVEY_KAT[i] for i in range(4))]
+    assert [int(v) for v in b.view(np.uint32)] == [k[1] for k in (SURVEY_KAT[i] for i in range(4))]
